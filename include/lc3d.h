@@ -1,0 +1,192 @@
+/*
+ * lc3d.h — C ABI of the B200-native fine-registration hot path.
+ *
+ * The reference (Eberty/LowCost3DReconstruction) has no FFI: its four hot-path
+ * tools call PCL classes directly.  This header is the boundary inserted at those
+ * PCL call sites.  Every entry point cites the reference line(s)
+ * whose PCL call it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Threading: one lc3d_ctx = one device + one stream; a ctx is not thread-safe,
+ * distinct ctxs are independent.  All calls are synchronous on return.
+ * Ownership: the caller owns every host buffer; the library owns device memory.
+ * Errors: 0 = ok, <0 = error (message via lc3d_last_error).  There is no CPU
+ * fallback: without a usable CUDA device lc3d_create fails.
+ */
+#ifndef LC3D_H_
+#define LC3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC3D_OK 0
+#define LC3D_ERR_INVALID (-1)
+#define LC3D_ERR_CUDA (-2)
+#define LC3D_ERR_NOMEM (-3)
+#define LC3D_ERR_INTERNAL (-4)
+
+/* A host point cloud described by base pointers + byte strides, so that both the
+ * PCL in-memory layout (pcl::PointXYZRGBNormal, 48-byte AoS: xyz at +0, normal at
+ * +16, rgba at +32, curvature at +36) and packed SoA arrays are accepted.
+ * normal / rgba / curvature may be NULL when the operation does not need them. */
+typedef struct lc3d_cloud {
+  int64_t n;
+  const float* xyz;
+  int64_t xyz_stride; /* bytes between consecutive points */
+  const float* normal;
+  int64_t normal_stride;
+  const uint32_t* rgba;
+  int64_t rgba_stride;
+  const float* curvature;
+  int64_t curvature_stride;
+} lc3d_cloud;
+
+typedef struct lc3d_ctx lc3d_ctx;
+/* A cloud staged on the device (SoA float4) — lets callers keep views resident in
+ * HBM across calls (chain registration re-uses each view as target then source). */
+typedef struct lc3d_dcloud lc3d_dcloud;
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current
+ * stream, so that the caller's CUDA events bracket our kernels) or NULL for a
+ * private stream. */
+int lc3d_create(int device, void* stream, lc3d_ctx** out);
+void lc3d_destroy(lc3d_ctx* ctx);
+/* ctx may be NULL: returns the last error of a failed lc3d_create on this thread. */
+const char* lc3d_last_error(const lc3d_ctx* ctx);
+const char* lc3d_version(void);
+/* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
+int64_t lc3d_launch_count(const lc3d_ctx* ctx);
+
+int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out);
+void lc3d_cloud_free(lc3d_ctx* ctx, lc3d_dcloud* dc);
+int64_t lc3d_dcloud_size(const lc3d_dcloud* dc);
+
+/* ------------------------------------------------------------------ ICP ---- */
+
+#define LC3D_ICP_POINT_TO_POINT 0 /* pcl::IterativeClosestPoint + TransformationEstimationSVD */
+#define LC3D_ICP_POINT_TO_PLANE 1 /* pcl::IterativeClosestPointWithNormals (PointToPlaneLLS)  */
+
+/* pcl::registration::DefaultConvergenceCriteria::ConvergenceState */
+#define LC3D_STATE_NOT_CONVERGED 0
+#define LC3D_STATE_ITERATIONS 1
+#define LC3D_STATE_TRANSFORM 2
+#define LC3D_STATE_ABS_MSE 3
+#define LC3D_STATE_REL_MSE 4
+#define LC3D_STATE_NO_CORRESPONDENCES 5
+
+/* Mirrors the setters at pcl_tools/fine_registration.cpp:112-118. */
+typedef struct lc3d_icp_params {
+  double max_correspondence_distance; /* :112 setMaxCorrespondenceDistance  (CLI default 0.1)  */
+  double transformation_epsilon;      /* :116 setTransformationEpsilon      (CLI default 1e-9) */
+  double euclidean_fitness_epsilon;   /* :118 setEuclideanFitnessEpsilon    (CLI default 1e-3) */
+  int32_t max_iterations;             /* :114 setMaximumIterations          (CLI default 50)   */
+  int32_t mode;                       /* LC3D_ICP_POINT_TO_POINT | LC3D_ICP_POINT_TO_PLANE     */
+  int32_t compute_fitness;            /* :126 getFitnessScore() (one extra unbounded NN pass)  */
+  int32_t dump_iteration;             /* parity hook: iteration (0-based) whose correspondences
+                                         are copied to corr_index/corr_dist2; -1 = none         */
+} lc3d_icp_params;
+
+typedef struct lc3d_icp_result {
+  float transformation[16]; /* :124 getFinalTransformation(), row-major 4x4 */
+  double fitness;           /* :126 getFitnessScore(): mean squared NN distance, all source pts */
+  double last_mse;          /* mean squared correspondence distance of the last iteration      */
+  int64_t last_correspondences;
+  int32_t converged;        /* :125 hasConverged() */
+  int32_t iterations;       /* nr_iterations_ */
+  int32_t state;            /* LC3D_STATE_* */
+  int32_t reserved;
+  /* device-side timings, CUDA events on the ctx stream, milliseconds */
+  float ms_upload;
+  float ms_index;   /* spatial index build over the target */
+  float ms_loop;    /* the ICP loop (all iterations) */
+  float ms_fitness; /* getFitnessScore pass */
+  float ms_download;
+  float ms_total;
+} lc3d_icp_result;
+
+/* Optional outputs of an alignment (any pointer may be NULL).
+ * registered_xyz / registered_normal: n_src x 3 packed floats — the `registered`
+ * cloud of fine_registration.cpp:121 (source transformed by the final matrix,
+ * normals rotated by its 3x3 block).  corr_index / corr_dist2: n_src entries, the
+ * correspondences of iteration params.dump_iteration in source order: index of
+ * the matched target point or -1 if rejected, and its squared distance. */
+typedef struct lc3d_icp_outputs {
+  float* registered_xyz;
+  float* registered_normal;
+  int32_t* corr_index;
+  float* corr_dist2;
+} lc3d_icp_outputs;
+
+/* Replaces icp.setInputSource/Target + align + getFinalTransformation +
+ * hasConverged + getFitnessScore (pcl_tools/fine_registration.cpp:105-126).
+ * Host buffers in, host buffers out; the whole loop runs on the device. */
+int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* target,
+                   const lc3d_icp_params* params, lc3d_icp_result* result,
+                   const lc3d_icp_outputs* outputs);
+
+/* Same, on clouds already resident in HBM.  Only the result record crosses PCIe. */
+int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d_dcloud* target,
+                            const lc3d_icp_params* params, lc3d_icp_result* result,
+                            const lc3d_icp_outputs* outputs);
+
+/* ------------------------------------------------------ neighbour search ---- */
+
+/* Exact k nearest neighbours of every query among `cloud` (pcl::search::KdTree
+ * nearestKSearch, normal_estimation.cpp:89-96; implicit in outlier_removal.cpp:80-84).
+ * out_index/out_dist2: n_query x k, ascending distance; ties broken by lower index.
+ * queries == NULL means the cloud queries itself (self is then neighbour 0). */
+int lc3d_knn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, int32_t k,
+             int32_t* out_index, float* out_dist2);
+
+/* Exact 1-NN with a max squared-distance gate (max_dist <= 0 or +inf: unbounded).
+ * out_index -1 where no neighbour passes the gate. */
+int lc3d_nn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, double max_dist,
+            int32_t* out_index, float* out_dist2);
+
+/* ------------------------------------------------------- normal estimation -- */
+
+/* Replaces pcl::NormalEstimation setKSearch + setViewPoint + compute
+ * (pcl_tools/normal_estimation.cpp:84-108).  out_normal: n x 3, out_curvature: n.
+ * The tool-level global flip (normal_estimation.cpp:112-118) stays in the caller. */
+int lc3d_normals(lc3d_ctx* ctx, const lc3d_cloud* cloud, int32_t k, const float viewpoint[3],
+                 float* out_normal, float* out_curvature);
+
+/* pcl::compute3DCentroid (normal_estimation.cpp:101): float32 mean of xyz. */
+int lc3d_centroid(lc3d_ctx* ctx, const lc3d_cloud* cloud, float out_centroid[4]);
+
+/* ------------------------------------------------------------- VoxelGrid ---- */
+
+/* Replaces pcl::VoxelGrid setLeafSize + filter (pcl_tools/cloud_downsampling.cpp:73-76).
+ * Outputs are caller-allocated for the worst case (n points): out_xyz n x 3,
+ * out_normal n x 3 (or NULL), out_rgba n (or NULL), out_curvature n (or NULL),
+ * out_voxel_of_point n (or NULL; voxel rank in output order of each input point).
+ * *out_count receives the number of output points.  When PCL's index-overflow
+ * guard trips (dx*dy*dz > INT32_MAX) the output is the unfiltered input, as in PCL. */
+int lc3d_voxel_grid(lc3d_ctx* ctx, const lc3d_cloud* cloud, const float leaf[3], float* out_xyz,
+                    float* out_normal, uint32_t* out_rgba, float* out_curvature,
+                    int32_t* out_voxel_of_point, int64_t* out_count);
+
+/* --------------------------------------------- StatisticalOutlierRemoval ---- */
+
+/* Replaces pcl::StatisticalOutlierRemoval setMeanK + setStddevMulThresh
+ * [+ setNegative] + filter (pcl_tools/outlier_removal.cpp:80-84, :91-93).
+ * out_kept_index: caller-allocated n entries, receives the kept indices in input
+ * order; *out_count their number.  out_mean_dist (n, or NULL): per-point mean
+ * neighbour distance.  out_stats (or NULL): {mean, stddev, threshold}. */
+int lc3d_sor(lc3d_ctx* ctx, const lc3d_cloud* cloud, int32_t mean_k, double stddev_mul,
+             int32_t negative, int32_t* out_kept_index, int64_t* out_count, float* out_mean_dist,
+             double out_stats[3]);
+
+/* ------------------------------------------------------------ transform ----- */
+
+/* pcl::transformPointCloudWithNormals (pcl_tools/transform.cpp:84-90; SURVEY §8f
+ * rank 1): xyz' = T * (xyz,1), n' = R * n, float32. matrix: row-major 4x4. */
+int lc3d_transform(lc3d_ctx* ctx, const lc3d_cloud* cloud, const float matrix[16], float* out_xyz,
+                   float* out_normal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC3D_H_ */

@@ -1,0 +1,344 @@
+"""Host-side mirror of the PCL interface the reference's hot-path tools call, over the C ABI.
+
+Function level (`icp_align`, `knn`, `normals`, `sor`, `voxel_grid`, `transform`) and PCL-named
+classes (`IterativeClosestPoint`, `NormalEstimation`, `VoxelGrid`,
+`StatisticalOutlierRemoval`) with the setters used at
+pcl_tools/fine_registration.cpp:105-126, normal_estimation.cpp:84-108,
+cloud_downsampling.cpp:73-76 and outlier_removal.cpp:80-93.  Everything computes on the GPU
+through liblc3d.so; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import HostCloud, IcpOutputs, IcpParams, IcpResult, POINT_TO_PLANE, POINT_TO_POINT
+
+
+class Lc3dError(RuntimeError):
+    pass
+
+
+class Context:
+    """One device + one stream (struct lc3d_ctx).  Not thread-safe; use one per thread/GPU."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        rc = self._lib.lc3d_create(int(device), C.c_void_p(stream or 0), C.byref(h))
+        if rc != 0:
+            raise Lc3dError(f"lc3d_create failed ({rc}): {self._lib.lc3d_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lc3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise Lc3dError(f"{what} failed ({rc}): {self._lib.lc3d_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.lc3d_launch_count(self._h))
+
+    # ---- resident clouds -------------------------------------------------------------
+    def upload(self, cloud) -> "DeviceCloud":
+        hc = _hc(cloud)
+        h = C.c_void_p()
+        self._check(self._lib.lc3d_cloud_upload(self._h, hc.ref(), C.byref(h)), "lc3d_cloud_upload")
+        return DeviceCloud(self, h, hc.n)
+
+
+class DeviceCloud:
+    def __init__(self, ctx: Context, handle, n: int):
+        self.ctx, self._h, self.n = ctx, handle, n
+
+    def free(self):
+        if self._h and self.ctx._h:
+            self.ctx._lib.lc3d_cloud_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None or _default_ctx._h is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _hc(x) -> HostCloud:
+    return x if isinstance(x, HostCloud) else HostCloud(x)
+
+
+def _result_dict(r: IcpResult) -> dict:
+    return dict(
+        transformation=np.array(r.transformation, dtype=np.float32).reshape(4, 4),
+        fitness=r.fitness, converged=bool(r.converged), iterations=int(r.iterations), state=int(r.state),
+        last_mse=r.last_mse, last_correspondences=int(r.last_correspondences),
+        ms=dict(upload=r.ms_upload, index=r.ms_index, loop=r.ms_loop, fitness=r.ms_fitness,
+                download=r.ms_download, total=r.ms_total),
+    )
+
+
+def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, transformation_epsilon=1e-9,
+              euclidean_fitness_epsilon=1e-3, mode=POINT_TO_POINT, compute_fitness=True, dump_iteration=-1,
+              want_registered=False, ctx: Context | None = None) -> dict:
+    """pcl::IterativeClosestPoint align + getFinalTransformation + hasConverged +
+    getFitnessScore (fine_registration.cpp:105-126).  src/tgt: arrays (n,3), HostCloud, or
+    DeviceCloud (both resident)."""
+    ctx = ctx or default_context()
+    p = IcpParams(float(max_correspondence_distance), float(transformation_epsilon),
+                  float(euclidean_fitness_epsilon), int(max_iterations), int(mode), int(bool(compute_fitness)),
+                  int(dump_iteration))
+    r = IcpResult()
+    o = IcpOutputs()
+    out = {}
+    resident = isinstance(src, DeviceCloud)
+    n = src.n if resident else _hc(src).n
+    if not resident:
+        src, tgt = _hc(src), _hc(tgt)
+    if dump_iteration >= 0:
+        out["corr_index"] = np.empty(n, dtype=np.int32)
+        out["corr_dist2"] = np.empty(n, dtype=np.float32)
+        o.corr_index = out["corr_index"].ctypes.data
+        o.corr_dist2 = out["corr_dist2"].ctypes.data
+    if want_registered:
+        out["registered_xyz"] = np.empty((n, 3), dtype=np.float32)
+        o.registered_xyz = out["registered_xyz"].ctypes.data
+        if resident or src.normal is not None:
+            out["registered_normal"] = np.empty((n, 3), dtype=np.float32)
+            o.registered_normal = out["registered_normal"].ctypes.data
+    if resident:
+        rc = ctx._lib.lc3d_icp_align_resident(ctx._h, src._h, tgt._h, C.byref(p), C.byref(r), C.byref(o))
+    else:
+        rc = ctx._lib.lc3d_icp_align(ctx._h, src.ref(), tgt.ref(), C.byref(p), C.byref(r), C.byref(o))
+    ctx._check(rc, "lc3d_icp_align")
+    out.update(_result_dict(r))
+    return out
+
+
+def nn(cloud, queries=None, max_dist: float = 0.0, ctx: Context | None = None):
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    q = c if queries is None else _hc(queries)
+    idx = np.empty(q.n, dtype=np.int32)
+    d2 = np.empty(q.n, dtype=np.float32)
+    ctx._check(ctx._lib.lc3d_nn(ctx._h, c.ref(), None if queries is None else q.ref(), float(max_dist),
+                                idx.ctypes.data, d2.ctypes.data), "lc3d_nn")
+    return idx, d2
+
+
+def knn(cloud, k: int, queries=None, ctx: Context | None = None):
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    q = c if queries is None else _hc(queries)
+    idx = np.empty((q.n, k), dtype=np.int32)
+    d2 = np.empty((q.n, k), dtype=np.float32)
+    ctx._check(ctx._lib.lc3d_knn(ctx._h, c.ref(), None if queries is None else q.ref(), int(k),
+                                 idx.ctypes.data, d2.ctypes.data), "lc3d_knn")
+    return idx, d2
+
+
+def centroid(cloud, ctx: Context | None = None) -> np.ndarray:
+    ctx = ctx or default_context()
+    out = (C.c_float * 4)()
+    ctx._check(ctx._lib.lc3d_centroid(ctx._h, _hc(cloud).ref(), out), "lc3d_centroid")
+    return np.array(out, dtype=np.float32)
+
+
+def normals(cloud, k: int, viewpoint=(0.0, 0.0, 0.0), ctx: Context | None = None):
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    vp = (C.c_float * 3)(*[float(v) for v in viewpoint])
+    nrm = np.empty((c.n, 3), dtype=np.float32)
+    curv = np.empty(c.n, dtype=np.float32)
+    ctx._check(ctx._lib.lc3d_normals(ctx._h, c.ref(), int(k), vp, nrm.ctypes.data, curv.ctypes.data),
+               "lc3d_normals")
+    return nrm, curv
+
+
+def sor(cloud, mean_k: int, stddev_mul: float, negative: bool = False, ctx: Context | None = None):
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    kept = np.empty(max(c.n, 1), dtype=np.int32)
+    cnt = C.c_int64(0)
+    md = np.empty(max(c.n, 1), dtype=np.float32)
+    stats = (C.c_double * 3)()
+    ctx._check(ctx._lib.lc3d_sor(ctx._h, c.ref(), int(mean_k), float(stddev_mul), int(bool(negative)),
+                                 kept.ctypes.data, C.byref(cnt), md.ctypes.data, stats), "lc3d_sor")
+    return kept[: cnt.value].copy(), md[: c.n], np.array(stats)
+
+
+def voxel_grid(cloud, leaf, ctx: Context | None = None) -> dict:
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    lf = (C.c_float * 3)(*([float(leaf)] * 3 if np.isscalar(leaf) else [float(v) for v in leaf]))
+    n = max(c.n, 1)
+    xyz = np.empty((n, 3), dtype=np.float32)
+    nrm = np.empty((n, 3), dtype=np.float32) if c.normal is not None else None
+    rgba = np.empty(n, dtype=np.uint32) if c.rgba is not None else None
+    curv = np.empty(n, dtype=np.float32) if c.curvature is not None else None
+    vox = np.empty(n, dtype=np.int32)
+    cnt = C.c_int64(0)
+    ctx._check(ctx._lib.lc3d_voxel_grid(
+        ctx._h, c.ref(), lf, xyz.ctypes.data, None if nrm is None else nrm.ctypes.data,
+        None if rgba is None else rgba.ctypes.data, None if curv is None else curv.ctypes.data,
+        vox.ctypes.data, C.byref(cnt)), "lc3d_voxel_grid")
+    m = cnt.value
+    return dict(xyz=xyz[:m].copy(), normal=None if nrm is None else nrm[:m].copy(),
+                rgba=None if rgba is None else rgba[:m].copy(),
+                curvature=None if curv is None else curv[:m].copy(), voxel_of_point=vox[: c.n])
+
+
+def transform(cloud, T, ctx: Context | None = None):
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    Tm = (C.c_float * 16)(*np.asarray(T, dtype=np.float32).reshape(16))
+    xyz = np.empty((c.n, 3), dtype=np.float32)
+    nrm = np.empty((c.n, 3), dtype=np.float32) if c.normal is not None else None
+    ctx._check(ctx._lib.lc3d_transform(ctx._h, c.ref(), Tm, xyz.ctypes.data,
+                                       None if nrm is None else nrm.ctypes.data), "lc3d_transform")
+    return xyz, nrm
+
+
+# ---------------------------------------------------------------- PCL-named classes ----
+
+class IterativeClosestPoint:
+    """pcl::IterativeClosestPoint<PointT,PointT> as used at fine_registration.cpp:105-126."""
+    _mode = POINT_TO_POINT
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+        self._src = self._tgt = None
+        self._max_corr = float(np.sqrt(np.finfo(np.float64).max))  # PCL default: sqrt(DBL_MAX)
+        self._max_iter = 10
+        self._teps = 0.0
+        self._feps = -np.finfo(np.float64).max
+        self._res = None
+
+    def setInputSource(self, cloud):
+        self._src = _hc(cloud)
+
+    def setInputTarget(self, cloud):
+        self._tgt = _hc(cloud)
+
+    def setMaxCorrespondenceDistance(self, d):
+        self._max_corr = float(d)
+
+    def setMaximumIterations(self, n):
+        self._max_iter = int(n)
+
+    def setTransformationEpsilon(self, e):
+        self._teps = float(e)
+
+    def setEuclideanFitnessEpsilon(self, e):
+        self._feps = float(e)
+
+    def align(self):
+        """Returns the registered cloud (xyz[, normals]) like icp.align(*registered)."""
+        if self._src is None or self._tgt is None:
+            raise Lc3dError("No input source/target given")
+        self._res = icp_align(self._src, self._tgt, self._max_corr, self._max_iter, self._teps, self._feps,
+                              mode=self._mode, compute_fitness=True, want_registered=True, ctx=self._ctx)
+        return self._res["registered_xyz"], self._res.get("registered_normal")
+
+    def getFinalTransformation(self):
+        return self._res["transformation"]
+
+    def hasConverged(self):
+        return self._res["converged"]
+
+    def getFitnessScore(self):
+        return self._res["fitness"]
+
+
+class IterativeClosestPointWithNormals(IterativeClosestPoint):
+    """pcl::IterativeClosestPointWithNormals (TransformationEstimationPointToPlaneLLS)."""
+    _mode = POINT_TO_PLANE
+
+
+class NormalEstimation:
+    """pcl::NormalEstimation as used at normal_estimation.cpp:84-108."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx, self._cloud, self._k, self._vp = ctx, None, 0, (0.0, 0.0, 0.0)
+
+    def setInputCloud(self, cloud):
+        self._cloud = _hc(cloud)
+
+    def setKSearch(self, k):
+        self._k = int(k)
+
+    def setViewPoint(self, x, y, z):
+        self._vp = (float(x), float(y), float(z))
+
+    def useSensorOriginAsViewPoint(self):
+        self._vp = (0.0, 0.0, 0.0)  # plain PLY clouds carry a zero sensor origin
+
+    def compute(self):
+        return normals(self._cloud, self._k, self._vp, ctx=self._ctx)
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid as used at cloud_downsampling.cpp:73-76."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx, self._cloud, self._leaf = ctx, None, (1.0, 1.0, 1.0)
+
+    def setInputCloud(self, cloud):
+        self._cloud = _hc(cloud)
+
+    def setLeafSize(self, lx, ly, lz):
+        self._leaf = (float(lx), float(ly), float(lz))
+
+    def filter(self):
+        return voxel_grid(self._cloud, self._leaf, ctx=self._ctx)
+
+
+class StatisticalOutlierRemoval:
+    """pcl::StatisticalOutlierRemoval as used at outlier_removal.cpp:80-93."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx, self._cloud, self._k, self._mul, self._neg = ctx, None, 1, 0.0, False
+
+    def setInputCloud(self, cloud):
+        self._cloud = _hc(cloud)
+
+    def setMeanK(self, k):
+        self._k = int(k)
+
+    def setStddevMulThresh(self, m):
+        self._mul = float(m)
+
+    def setNegative(self, neg):
+        self._neg = bool(neg)
+
+    def filter(self):
+        """Returns the kept indices (input order)."""
+        return sor(self._cloud, self._k, self._mul, self._neg, ctx=self._ctx)[0]

@@ -1,0 +1,418 @@
+// capi.cu — the C ABI of include/lc3d.h over the CUDA kernels.  No CPU fallback.
+#include <cfloat>
+#include <cmath>
+#include <limits>
+
+#include "common.cuh"
+#include "grid.cuh"
+#include "icp.cuh"
+#include "knn.cuh"
+#include "scan_sort.cuh"
+#include "search.cuh"
+#include "voxel.cuh"
+
+using namespace lc3d;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// scratch slots beyond the grid builder's
+enum {
+  kScrRawA = kScrGridEnd, kScrRawB, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
+  kScrOutB, kScrDumpIdx, kScrDumpD2, kScrQuery, kScrMisc, kScrMisc2, kScrMisc3, kScrEnd
+};
+static_assert(kScrEnd <= 32, "scratch slots");
+
+struct Guard {  // sets the device for the duration of a call
+  explicit Guard(lc3d_ctx* c) { LC3D_CUDA(cudaSetDevice(c->device)); }
+};
+
+// Strided host floats -> device float4.  elems = 3 (xyz -> w=1) or 3+1 (normal + curvature).
+__global__ void __launch_bounds__(256)
+    unpack_strided(const unsigned char* __restrict__ raw, int64_t stride, int n, float w_default,
+                   const unsigned char* __restrict__ raw_w, int64_t stride_w,
+                   float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+  float4 v;
+  v.x = p[0];
+  v.y = p[1];
+  v.z = p[2];
+  v.w = raw_w ? *reinterpret_cast<const float*>(raw_w + (size_t)i * stride_w) : w_default;
+  out[i] = v;
+}
+
+// Copies n records of `rec` bytes at `stride` from host memory into a device raw buffer
+// and returns the device pointer + the stride to use there.
+const unsigned char* stage_raw(lc3d_ctx* ctx, DevBuf& buf, const void* host, int64_t stride,
+                               int64_t n, int rec) {
+  if (n == 0) return nullptr;
+  size_t bytes = (size_t)(n - 1) * stride + rec;
+  buf.ensure(bytes + 16);
+  LC3D_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return buf.as<unsigned char>();
+}
+
+void upload_cloud(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals) {
+  const int64_t n = h->n;
+  d->n = n;
+  d->has_normal = false;
+  if (n == 0) return;
+  if (n > (int64_t)INT32_MAX / 2) throw CudaError{"cloud too large (n must be < 2^30)"};
+  if (!h->xyz || h->xyz_stride < 12) throw CudaError{"cloud.xyz is NULL or xyz_stride < 12"};
+  d->xyz.ensure((size_t)n * 16);
+  const unsigned char* raw = stage_raw(ctx, ctx->scratch[kScrRawA], h->xyz, h->xyz_stride, n, 12);
+  LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, raw, h->xyz_stride, (int)n, 1.0f,
+              (const unsigned char*)nullptr, (int64_t)0, d->xyz.as<float4>());
+  if (want_normals && h->normal) {
+    if (h->normal_stride < 12) throw CudaError{"normal_stride < 12"};
+    d->normal.ensure((size_t)n * 16);
+    const unsigned char* rawn;
+    // same AoS block as xyz (PCL 48-byte points)?  then the staged copy already has them
+    const ptrdiff_t off = (const char*)h->normal - (const char*)h->xyz;
+    if (h->normal_stride == h->xyz_stride && off >= 0 && off + 12 <= h->xyz_stride) {
+      // the raw copy covered (n-1)*stride + 12 bytes from xyz; normals of the last record
+      // may lie beyond it, so stage the tail explicitly
+      size_t have = (size_t)(n - 1) * h->xyz_stride + 12;
+      size_t need = (size_t)(n - 1) * h->xyz_stride + off + 12;
+      if (need > have) {
+        ctx->scratch[kScrRawA].ensure(need + 16);  // no-op: ensure() over-allocates by >= 256 B
+        LC3D_CUDA(cudaMemcpyAsync(ctx->scratch[kScrRawA].as<unsigned char>() + have,
+                                  (const char*)h->xyz + have, need - have, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+      }
+      rawn = ctx->scratch[kScrRawA].as<unsigned char>() + off;
+    } else {
+      rawn = stage_raw(ctx, ctx->scratch[kScrRawB], h->normal, h->normal_stride, n, 12);
+    }
+    LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, rawn, h->normal_stride, (int)n, 0.0f,
+                (const unsigned char*)nullptr, (int64_t)0, d->normal.as<float4>());
+    d->has_normal = true;
+  }
+}
+
+float gate_from_distance(double max_dist) {
+  if (!(max_dist > 0) || std::isinf(max_dist)) return INFINITY;
+  double d2 = max_dist * max_dist;
+  if (d2 >= (double)FLT_MAX) return INFINITY;
+  float g = (float)d2;
+  if ((double)g > d2) g = std::nextafterf(g, 0.0f);
+  return g;  // largest float with (double)g <= max_dist^2: "d2 > max^2" rejects exactly as PCL
+}
+
+double cell_factor_env() {
+  const char* e = std::getenv("LC3D_CELL_FACTOR");
+  double f = e ? std::atof(e) : 2.0;
+  return f > 0.1 ? f : 2.0;
+}
+
+void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, const lc3d_icp_params* p,
+             lc3d_icp_result* res, const lc3d_icp_outputs* out) {
+  cudaStream_t st = ctx->stream;
+  const int n = (int)src->n;
+  if (p->max_iterations <= 0) throw CudaError{"max_iterations needs to be greater than zero."};
+  if (p->mode != LC3D_ICP_POINT_TO_POINT && p->mode != LC3D_ICP_POINT_TO_PLANE)
+    throw CudaError{"unknown ICP mode"};
+  if (p->mode == LC3D_ICP_POINT_TO_PLANE && tgt->n > 0 && !tgt->has_normal)
+    throw CudaError{"point-to-plane ICP needs target normals"};
+  // ---- spatial index over the target (KdTreeFLANN::setInputCloud) ----
+  ctx->tm[1].start(st);
+  Grid& G = *ctx->grid;
+  grid_build(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr,
+             tgt->n, cell_factor_env());
+  ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
+  ctx->scratch[kScrSrcWork].ensure((size_t)n * 16 + 16);
+  float4* X0 = ctx->scratch[kScrSrcSorted].as<float4>();
+  float4* X = ctx->scratch[kScrSrcWork].as<float4>();
+  sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0);
+  if (n > 0) LC3D_CUDA(cudaMemcpyAsync(X, X0, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+  ctx->tm[1].stop(st);
+  // ---- the loop ----
+  ctx->scratch[kScrState].ensure(sizeof(IcpState));
+  IcpState* d_state = ctx->scratch[kScrState].as<IcpState>();
+  const int nblk = std::max(1, div_up(n, kIcpThreads));
+  ctx->scratch[kScrPartials].ensure((size_t)kNvP2Plane * nblk * 8);
+  double* partials = ctx->scratch[kScrPartials].as<double>();
+  IcpConfig cfg;
+  cfg.gate = gate_from_distance(p->max_correspondence_distance);
+  cfg.max_iterations = p->max_iterations;
+  cfg.rot_thr = 1.0 - p->transformation_epsilon;
+  cfg.transl_thr = p->transformation_epsilon;
+  cfg.rel_mse = p->euclidean_fitness_epsilon;
+  cfg.abs_mse = 1e-12;
+  cfg.dump_iteration = p->dump_iteration;
+  cfg.mode = p->mode;
+  int32_t* d_dump_idx = nullptr;
+  float* d_dump_d2 = nullptr;
+  const bool dump = out && (out->corr_index || out->corr_dist2) && p->dump_iteration >= 0 && n > 0;
+  if (dump) {
+    ctx->scratch[kScrDumpIdx].ensure((size_t)n * 4);
+    ctx->scratch[kScrDumpD2].ensure((size_t)n * 4);
+    d_dump_idx = ctx->scratch[kScrDumpIdx].as<int32_t>();
+    d_dump_d2 = ctx->scratch[kScrDumpD2].as<float>();
+    LC3D_CUDA(cudaMemsetAsync(d_dump_idx, 0xff, (size_t)n * 4, st));
+    LC3D_CUDA(cudaMemsetAsync(d_dump_d2, 0x7f, (size_t)n * 4, st));
+  }
+  ctx->tm[2].start(st);
+  LC3D_LAUNCH(ctx, icp_state_init, 1, 32, 0, d_state);
+  for (int it = 0; it < p->max_iterations; ++it) {
+    if (p->mode == LC3D_ICP_POINT_TO_PLANE)
+      LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state,
+                  cfg, G.v, X, n, partials, d_dump_idx, d_dump_d2);
+    else
+      LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT>, nblk, kIcpThreads, 0, d_state,
+                  cfg, G.v, X, n, partials, d_dump_idx, d_dump_d2);
+  }
+  ctx->tm[2].stop(st);
+  // ---- getFitnessScore ----
+  ctx->tm[3].start(st);
+  if (p->compute_fitness)
+    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk, kIcpThreads, 0, d_state, G.v, X0, n, partials);
+  ctx->tm[3].stop(st);
+  // ---- results ----
+  ctx->tm[4].start(st);
+  ctx->pinned[0].ensure(sizeof(IcpState));
+  IcpState* h_state = ctx->pinned[0].as<IcpState>();
+  LC3D_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
+  if (out && out->registered_xyz && n > 0) {
+    ctx->scratch[kScrOutA].ensure((size_t)n * 12);
+    const bool wn = out->registered_normal && src->has_normal;
+    if (wn) ctx->scratch[kScrOutB].ensure((size_t)n * 12);
+    LC3D_LAUNCH(ctx, transform_kernel, div_up(n, 256), 256, 0, d_state->Tfinal,
+                src->xyz.as<float4>(), wn ? src->normal.as<float4>() : nullptr, n,
+                ctx->scratch[kScrOutA].as<float>(), wn ? ctx->scratch[kScrOutB].as<float>() : nullptr);
+    LC3D_CUDA(cudaMemcpyAsync(out->registered_xyz, ctx->scratch[kScrOutA].p, (size_t)n * 12,
+                              cudaMemcpyDeviceToHost, st));
+    if (wn)
+      LC3D_CUDA(cudaMemcpyAsync(out->registered_normal, ctx->scratch[kScrOutB].p, (size_t)n * 12,
+                                cudaMemcpyDeviceToHost, st));
+  }
+  if (dump) {
+    if (out->corr_index)
+      LC3D_CUDA(cudaMemcpyAsync(out->corr_index, d_dump_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (out->corr_dist2)
+      LC3D_CUDA(cudaMemcpyAsync(out->corr_dist2, d_dump_d2, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  }
+  ctx->tm[4].stop(st);
+  ctx->tm[5].stop(st);
+  LC3D_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(res->transformation, h_state->Tfinal, sizeof res->transformation);
+  res->converged = h_state->converged;
+  res->iterations = h_state->iter;
+  res->state = h_state->state;
+  res->last_mse = h_state->last_mse;
+  res->last_correspondences = h_state->last_corr;
+  res->fitness = 0.0;
+  if (p->compute_fitness)
+    res->fitness = h_state->fitness_cnt > 0 ? h_state->fitness_sum / (double)h_state->fitness_cnt
+                                            : std::numeric_limits<double>::max();
+  res->ms_index = ctx->tm[1].ms();
+  res->ms_loop = ctx->tm[2].ms();
+  res->ms_fitness = ctx->tm[3].ms();
+  res->ms_download = ctx->tm[4].ms();
+  res->ms_total = ctx->tm[5].ms();
+}
+
+template <typename F>
+int guarded(lc3d_ctx* ctx, F&& f) {
+  if (!ctx) return LC3D_ERR_INVALID;
+  try {
+    Guard g(ctx);
+    f();
+    return LC3D_OK;
+  } catch (const CudaError& e) {
+    ctx->err = e.msg;
+    cudaGetLastError();
+    return e.msg.find("failed at") != std::string::npos ? LC3D_ERR_CUDA : LC3D_ERR_INVALID;
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return LC3D_ERR_INTERNAL;
+  }
+}
+
+struct TmpClouds {
+  lc3d_dcloud &a, &b;
+};
+TmpClouds tmp_clouds(lc3d_ctx* ctx) { return TmpClouds{ctx->tmp_a, ctx->tmp_b}; }
+Grid& ctx_grid(lc3d_ctx* ctx) { return *ctx->grid; }
+
+}  // namespace
+
+extern "C" {
+
+const char* lc3d_version(void) { return "lc3d-b200 0.1 (sm_100a)"; }
+
+int lc3d_create(int device, void* stream, lc3d_ctx** out) {
+  if (!out) return LC3D_ERR_INVALID;
+  *out = nullptr;
+  lc3d_ctx* ctx = nullptr;
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw CudaError{std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                      "); lc3d has no CPU fallback"};
+    if (device < 0 || device >= count) throw CudaError{"invalid device ordinal"};
+    LC3D_CUDA(cudaSetDevice(device));
+    ctx = new lc3d_ctx;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    LC3D_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+      ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+      ctx->own_stream = false;
+    } else {
+      LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    for (auto& t : ctx->tm) t.init();
+    ctx->grid = new Grid;
+    *out = ctx;
+    return LC3D_OK;
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    cudaGetLastError();
+    delete ctx;
+    return LC3D_ERR_CUDA;
+  }
+}
+
+void lc3d_destroy(lc3d_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->scratch) b.release();
+  for (auto& b : ctx->pinned) b.release();
+  ctx->tmp_a.release();
+  ctx->tmp_b.release();
+  if (ctx->grid) {
+    ctx->grid->release();
+    delete ctx->grid;
+  }
+  for (auto& t : ctx->tm) t.destroy();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lc3d_last_error(const lc3d_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int64_t lc3d_launch_count(const lc3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out) {
+  if (!out || !host) return LC3D_ERR_INVALID;
+  *out = nullptr;
+  lc3d_dcloud* d = new lc3d_dcloud;
+  int rc = guarded(ctx, [&] {
+    upload_cloud(ctx, host, d, true);
+    LC3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+  if (rc != LC3D_OK) {
+    d->release();
+    delete d;
+    return rc;
+  }
+  *out = d;
+  return LC3D_OK;
+}
+
+void lc3d_cloud_free(lc3d_ctx* ctx, lc3d_dcloud* dc) {
+  if (!dc) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  dc->release();
+  delete dc;
+}
+
+int64_t lc3d_dcloud_size(const lc3d_dcloud* dc) { return dc ? dc->n : 0; }
+
+int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* target,
+                   const lc3d_icp_params* params, lc3d_icp_result* result,
+                   const lc3d_icp_outputs* outputs) {
+  if (!source || !target || !params || !result) return LC3D_ERR_INVALID;
+  return guarded(ctx, [&] {
+    std::memset(result, 0, sizeof *result);
+    TmpClouds tc = tmp_clouds(ctx);
+    ctx->tm[5].start(ctx->stream);
+    ctx->tm[0].start(ctx->stream);
+    const bool need_src_normals = outputs && outputs->registered_normal;
+    upload_cloud(ctx, source, &tc.a, need_src_normals);
+    upload_cloud(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE);
+    ctx->tm[0].stop(ctx->stream);
+    icp_run(ctx, &tc.a, &tc.b, params, result, outputs);
+    result->ms_upload = ctx->tm[0].ms();
+  });
+}
+
+int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d_dcloud* target,
+                            const lc3d_icp_params* params, lc3d_icp_result* result,
+                            const lc3d_icp_outputs* outputs) {
+  if (!source || !target || !params || !result) return LC3D_ERR_INVALID;
+  return guarded(ctx, [&] {
+    std::memset(result, 0, sizeof *result);
+    ctx->tm[5].start(ctx->stream);
+    icp_run(ctx, source, target, params, result, outputs);
+  });
+}
+
+int lc3d_nn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, double max_dist,
+            int32_t* out_index, float* out_dist2) {
+  if (!cloud || !out_index || !out_dist2) return LC3D_ERR_INVALID;
+  return guarded(ctx, [&] {
+    TmpClouds tc = tmp_clouds(ctx);
+    upload_cloud(ctx, cloud, &tc.b, false);
+    const lc3d_dcloud* q = &tc.b;
+    if (queries) {
+      upload_cloud(ctx, queries, &tc.a, false);
+      q = &tc.a;
+    }
+    const int n = (int)q->n;
+    if (n == 0) return;
+    Grid& G = ctx_grid(ctx);
+    grid_build(ctx, G, tc.b.xyz.as<float4>(), nullptr, tc.b.n, cell_factor_env());
+    ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
+    float4* Q = ctx->scratch[kScrSrcSorted].as<float4>();
+    sort_queries_by_cell(ctx, G, q->xyz.as<float4>(), n, Q);
+    ctx->scratch[kScrDumpIdx].ensure((size_t)n * 4);
+    ctx->scratch[kScrDumpD2].ensure((size_t)n * 4);
+    LC3D_LAUNCH(ctx, nn_kernel, div_up(n, 256), 256, 0, G.v, Q, n, gate_from_distance(max_dist),
+                ctx->scratch[kScrDumpIdx].as<int32_t>(), ctx->scratch[kScrDumpD2].as<float>());
+    LC3D_CUDA(cudaMemcpyAsync(out_index, ctx->scratch[kScrDumpIdx].p, (size_t)n * 4,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    LC3D_CUDA(cudaMemcpyAsync(out_dist2, ctx->scratch[kScrDumpD2].p, (size_t)n * 4,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    LC3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int lc3d_transform(lc3d_ctx* ctx, const lc3d_cloud* cloud, const float matrix[16], float* out_xyz,
+                   float* out_normal) {
+  if (!cloud || !matrix || !out_xyz) return LC3D_ERR_INVALID;
+  return guarded(ctx, [&] {
+    TmpClouds tc = tmp_clouds(ctx);
+    upload_cloud(ctx, cloud, &tc.a, out_normal != nullptr);
+    const int n = (int)tc.a.n;
+    if (n == 0) return;
+    ctx->scratch[kScrMisc].ensure(64);
+    LC3D_CUDA(cudaMemcpyAsync(ctx->scratch[kScrMisc].p, matrix, 64, cudaMemcpyHostToDevice, ctx->stream));
+    const bool wn = out_normal && tc.a.has_normal;
+    ctx->scratch[kScrOutA].ensure((size_t)n * 12);
+    if (wn) ctx->scratch[kScrOutB].ensure((size_t)n * 12);
+    LC3D_LAUNCH(ctx, transform_kernel, div_up(n, 256), 256, 0, ctx->scratch[kScrMisc].as<float>(),
+                tc.a.xyz.as<float4>(), wn ? tc.a.normal.as<float4>() : nullptr, n,
+                ctx->scratch[kScrOutA].as<float>(), wn ? ctx->scratch[kScrOutB].as<float>() : nullptr);
+    LC3D_CUDA(cudaMemcpyAsync(out_xyz, ctx->scratch[kScrOutA].p, (size_t)n * 12, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    if (wn)
+      LC3D_CUDA(cudaMemcpyAsync(out_normal, ctx->scratch[kScrOutB].p, (size_t)n * 12,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    LC3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+#include "capi_filters.inc"
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// common.cuh — context, device buffers, error handling, exact-float helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lc3d.h"
+
+namespace lc3d {
+
+constexpr int kNumSmsB200 = 148;
+
+struct CudaError {
+  std::string msg;
+};
+
+#define LC3D_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      throw ::lc3d::CudaError{std::string(#expr) + " failed at " + __FILE__ + ":" +           \
+                              std::to_string(__LINE__) + ": " + cudaGetErrorString(_e)};      \
+    }                                                                                         \
+  } while (0)
+
+// Grow-only device buffer; reused across calls so the steady state allocates nothing.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) LC3D_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    LC3D_CUDA(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) LC3D_CUDA(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    LC3D_CUDA(cudaMallocHost(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  void init() {
+    LC3D_CUDA(cudaEventCreate(&a));
+    LC3D_CUDA(cudaEventCreate(&b));
+  }
+  void destroy() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    a = b = nullptr;
+  }
+  void start(cudaStream_t s) { LC3D_CUDA(cudaEventRecord(a, s)); }
+  void stop(cudaStream_t s) { LC3D_CUDA(cudaEventRecord(b, s)); }
+  float ms() {
+    float v = 0;
+    LC3D_CUDA(cudaEventSynchronize(b));
+    LC3D_CUDA(cudaEventElapsedTime(&v, a, b));
+    return v;
+  }
+};
+
+// ---- exact float32 helpers: every parity-critical expression is written with the
+// round-to-nearest intrinsics so that nvcc never contracts it into an FMA
+// (PCL/FLANN distro builds evaluate mul and add separately).
+__device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float px, float py,
+                                             float pz) {
+  float d = __fsub_rn(qx, px);
+  float r = __fmul_rn(d, d);
+  d = __fsub_rn(qy, py);
+  r = __fadd_rn(r, __fmul_rn(d, d));
+  d = __fsub_rn(qz, pz);
+  r = __fadd_rn(r, __fmul_rn(d, d));
+  return r;
+}
+
+// row r of T times (x,y,z,1): ((T0*x + T1*y) + T2*z) + T3, float32, no FMA.
+__device__ __forceinline__ float xform_row(const float* __restrict__ T, int r, float x, float y,
+                                           float z) {
+  float s = __fmul_rn(T[r * 4 + 0], x);
+  s = __fadd_rn(s, __fmul_rn(T[r * 4 + 1], y));
+  s = __fadd_rn(s, __fmul_rn(T[r * 4 + 2], z));
+  return __fadd_rn(s, T[r * 4 + 3]);
+}
+__device__ __forceinline__ float rot_row(const float* __restrict__ T, int r, float x, float y,
+                                         float z) {
+  float s = __fmul_rn(T[r * 4 + 0], x);
+  s = __fadd_rn(s, __fmul_rn(T[r * 4 + 1], y));
+  return __fadd_rn(s, __fmul_rn(T[r * 4 + 2], z));
+}
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+  return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace lc3d
+
+namespace lc3d {
+struct Grid;
+}
+
+struct lc3d_dcloud {
+  int64_t n = 0;
+  lc3d::DevBuf xyz;     // float4 (x,y,z,1) in input order
+  lc3d::DevBuf normal;  // float4 (nx,ny,nz,0) in input order, or empty
+  bool has_normal = false;
+  void release() {
+    xyz.release();
+    normal.release();
+    n = 0;
+    has_normal = false;
+  }
+};
+
+// The opaque context of include/lc3d.h.
+struct lc3d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = lc3d::kNumSmsB200;
+  lc3d::DevBuf scratch[32];  // grow-only scratch arena, slots named by the users
+  lc3d::PinnedBuf pinned[2];
+  lc3d::Timer tm[6];
+  lc3d::Grid* grid = nullptr;  // spatial index reused across calls
+  lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
+};
+
+#define LC3D_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+  do {                                                                        \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+    ++(ctx)->launches;                                                        \
+    LC3D_CUDA(cudaGetLastError());                                            \
+  } while (0)

@@ -1,0 +1,364 @@
+// grid.cuh — uniform-grid spatial index over a cloud (replaces pcl::search::KdTree /
+// KdTreeFLANN: implicit in icp.setInputTarget, fine_registration.cpp:109; explicit at
+// normal_estimation.cpp:89-90).
+//
+// Layout in HBM (all SoA, 16-byte vector loads):
+//   pts[j]        float4 (x, y, z, bits(original index)), sorted by linear cell id
+//                 (x fastest), stable => ascending original index inside a cell
+//   nrm[j]        float4 (nx, ny, nz, curvature) in the same order (optional)
+//   cell_start[c] uint32, ncell+1 entries: points of cell c are [cell_start[c], cell_start[c+1]).
+//                 Because x is the fastest-varying cell coordinate, a run of cells
+//                 along x is ONE contiguous point range: a 3x3x3 neighbourhood is 9
+//                 (start,end) lookups, not 27.
+//   coarse_cnt[C] uint32 occupancy of 8x8x8-cell super-cells: far-field rejection and
+//                 ring expansion run on this small table.
+// Build: bbox reduce -> density probe -> cell keys (+histogram) -> hand-written radix
+// sort -> exclusive scan of the histogram -> gather.
+#pragma once
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace lc3d {
+
+constexpr int kCoarseShift = 3;  // super-cell = 8^3 cells
+constexpr int kCoarse = 1 << kCoarseShift;
+constexpr float kCellSlack = 1e-3f;  // cells; covers float rounding of cell coordinates
+constexpr int kMaxDim = 2048;
+constexpr int64_t kMaxCells = (int64_t)1 << 26;
+
+struct GridDev {
+  float ox, oy, oz;
+  float c, inv_c;
+  int dx, dy, dz;
+  int cdx, cdy, cdz;
+  int n;  // finite points indexed
+  const uint32_t* cell_start;
+  const uint32_t* coarse_cnt;
+  const float4* pts;
+  const float4* nrm;
+};
+
+struct Grid {
+  GridDev v{};
+  DevBuf cell_start, coarse_cnt, pts, nrm;
+  int64_t ncell = 0;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  void release() {
+    cell_start.release();
+    coarse_cnt.release();
+    pts.release();
+    nrm.release();
+  }
+};
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+inline float ord2f(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+struct BBoxOut {
+  uint32_t lo[3], hi[3];
+  uint32_t count;
+  uint32_t pad;
+};
+
+__global__ void bbox_init(BBoxOut* o) {
+  if (threadIdx.x == 0) {
+    o->lo[0] = o->lo[1] = o->lo[2] = 0xffffffffu;
+    o->hi[0] = o->hi[1] = o->hi[2] = 0u;
+    o->count = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) bbox_reduce(const float4* __restrict__ p, int n, BBoxOut* o) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  uint32_t cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 q = p[i];
+    if (finite3(q.x, q.y, q.z)) {
+      lo[0] = fminf(lo[0], q.x); hi[0] = fmaxf(hi[0], q.x);
+      lo[1] = fminf(lo[1], q.y); hi[1] = fmaxf(hi[1], q.y);
+      lo[2] = fminf(lo[2], q.z); hi[2] = fmaxf(hi[2], q.z);
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], __shfl_down_sync(0xffffffffu, lo[d], o2));
+      hi[d] = fmaxf(hi[d], __shfl_down_sync(0xffffffffu, hi[d], o2));
+    }
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o2);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&o->lo[d], f2ord(lo[d]));
+      atomicMax(&o->hi[d], f2ord(hi[d]));
+    }
+    atomicAdd(&o->count, cnt);
+  }
+}
+
+// Density probe: occupancy bitmask of a 64^3 grid over the bbox; the number of occupied
+// probe cells estimates the sampled surface area and hence the point spacing.
+constexpr int kProbe = 64;
+__global__ void __launch_bounds__(256)
+    probe_mark(const float4* __restrict__ p, int n, float ox, float oy, float oz, float sx, float sy,
+               float sz, uint32_t* __restrict__ bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = p[i];
+  if (!finite3(q.x, q.y, q.z)) return;
+  int ix = min(max((int)((q.x - ox) * sx), 0), kProbe - 1);
+  int iy = min(max((int)((q.y - oy) * sy), 0), kProbe - 1);
+  int iz = min(max((int)((q.z - oz) * sz), 0), kProbe - 1);
+  int c = (iz * kProbe + iy) * kProbe + ix;
+  uint32_t m = 1u << (c & 31);
+  if (!(bits[c >> 5] & m)) atomicOr(&bits[c >> 5], m);
+}
+__global__ void __launch_bounds__(256) probe_count(const uint32_t* __restrict__ bits, int nwords,
+                                                   uint32_t* out) {
+  uint32_t c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x)
+    c += __popc(bits[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// Cell coordinate (in cells, float) — the single definition used for build and query.
+__device__ __forceinline__ float cell_coord(float v, float o, float inv_c) {
+  return __fmul_rn(__fsub_rn(v, o), inv_c);
+}
+
+// key = linear cell id (x fastest); non-finite points get the sentinel `ncell`.
+// Also histograms the cells (-> cell_start by scan) and the 8^3 super-cells.
+__global__ void __launch_bounds__(256)
+    grid_keys(const float4* __restrict__ p, int n, GridDev g, uint32_t ncell,
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+              uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ coarse_cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = p[i];
+  uint32_t key = ncell;
+  if (finite3(q.x, q.y, q.z)) {
+    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
+    int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
+    int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
+    key = (uint32_t)((iz * g.dy + iy) * g.dx + ix);
+    if (cell_cnt) atomicAdd(&cell_cnt[key], 1u);
+    if (coarse_cnt)
+      atomicAdd(&coarse_cnt[((iz >> kCoarseShift) * g.cdy + (iy >> kCoarseShift)) * g.cdx +
+                            (ix >> kCoarseShift)],
+                1u);
+  }
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+    gather_sorted(const float4* __restrict__ p, const float4* __restrict__ nrm,
+                  const uint32_t* __restrict__ vals, int n, float4* __restrict__ out_p,
+                  float4* __restrict__ out_n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t i = vals[j];
+  float4 q = p[i];
+  q.w = __int_as_float((int)i);
+  out_p[j] = q;
+  if (nrm) out_n[j] = nrm[i];
+}
+
+inline int bit_length(uint32_t v) {
+  int b = 0;
+  while (v) {
+    ++b;
+    v >>= 1;
+  }
+  return b;
+}
+
+// Scratch slots of ctx->scratch used by the index build.
+enum { kScrBBox = 0, kScrProbe, kScrKeys, kScrVals, kScrKeysAlt, kScrValsAlt, kScrHist, kScrScan,
+       kScrGridEnd };
+
+// Builds the grid over `xyz` (n float4, input order).  cell_factor: cell edge in units of
+// the estimated point spacing.  min_cell > 0 forces a lower bound on the cell edge.
+inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
+                       double cell_factor, double min_cell = 0.0) {
+  const int n = (int)n64;
+  cudaStream_t st = ctx->stream;
+  G.v = GridDev{};
+  if (n == 0) {
+    G.v.dx = G.v.dy = G.v.dz = G.v.cdx = G.v.cdy = G.v.cdz = 1;
+    G.v.c = G.v.inv_c = 1.0f;
+    G.ncell = 1;
+    G.cell_start.ensure(2 * 4);
+    G.coarse_cnt.ensure(4);
+    G.pts.ensure(16);
+    LC3D_CUDA(cudaMemsetAsync(G.cell_start.p, 0, 8, st));
+    LC3D_CUDA(cudaMemsetAsync(G.coarse_cnt.p, 0, 4, st));
+    G.v.cell_start = G.cell_start.as<uint32_t>();
+    G.v.coarse_cnt = G.coarse_cnt.as<uint32_t>();
+    G.v.pts = G.pts.as<float4>();
+    return;
+  }
+  // 1. bounding box of the finite points
+  ctx->scratch[kScrBBox].ensure(sizeof(BBoxOut) + 16);
+  BBoxOut* d_bb = ctx->scratch[kScrBBox].as<BBoxOut>();
+  LC3D_LAUNCH(ctx, bbox_init, 1, 32, 0, d_bb);
+  int nb = std::min(div_up(n, 256), ctx->num_sms * 8);
+  LC3D_LAUNCH(ctx, bbox_reduce, nb, 256, 0, xyz, n, d_bb);
+  BBoxOut bb;
+  LC3D_CUDA(cudaMemcpyAsync(&bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, st));
+  LC3D_CUDA(cudaStreamSynchronize(st));
+  const int nfinite = (int)bb.count;
+  double ext[3];
+  if (nfinite == 0) {
+    for (int d = 0; d < 3; ++d) G.lo[d] = G.hi[d] = 0.0f;
+  } else {
+    for (int d = 0; d < 3; ++d) {
+      G.lo[d] = ord2f(bb.lo[d]);
+      G.hi[d] = ord2f(bb.hi[d]);
+    }
+  }
+  double maxext = 0;
+  for (int d = 0; d < 3; ++d) {
+    ext[d] = (double)G.hi[d] - (double)G.lo[d];
+    maxext = std::max(maxext, ext[d]);
+  }
+  // 2. density probe -> point spacing -> cell edge
+  double cell;
+  if (nfinite <= 1 || maxext <= 0) {
+    cell = maxext > 0 ? maxext : 1.0;
+  } else {
+    double pe[3];
+    for (int d = 0; d < 3; ++d) pe[d] = std::max(ext[d], maxext * 1e-6) / kProbe;
+    const int nwords = kProbe * kProbe * kProbe / 32;
+    ctx->scratch[kScrProbe].ensure(nwords * 4 + 16);
+    uint32_t* bits = ctx->scratch[kScrProbe].as<uint32_t>();
+    LC3D_CUDA(cudaMemsetAsync(bits, 0, nwords * 4 + 16, st));
+    LC3D_LAUNCH(ctx, probe_mark, div_up(n, 256), 256, 0, xyz, n, G.lo[0], G.lo[1], G.lo[2],
+                (float)(1.0 / pe[0]), (float)(1.0 / pe[1]), (float)(1.0 / pe[2]), bits);
+    LC3D_LAUNCH(ctx, probe_count, 32, 256, 0, bits, nwords, bits + nwords);
+    uint32_t occ = 0;
+    LC3D_CUDA(cudaMemcpyAsync(&occ, bits + nwords, 4, cudaMemcpyDeviceToHost, st));
+    LC3D_CUDA(cudaStreamSynchronize(st));
+    double cell_area = std::pow(pe[0] * pe[1] * pe[2], 2.0 / 3.0);
+    double area = std::max(1.0, (double)occ) * cell_area;
+    double spacing = std::sqrt(area / (double)nfinite);
+    cell = cell_factor * spacing;
+  }
+  cell = std::max(cell, min_cell);
+  cell = std::max(cell, maxext / (kMaxDim - 2));
+  cell = std::max(cell, 1e-30);
+  int dims[3];
+  for (int iter = 0; iter < 64; ++iter) {
+    int64_t tot = 1;
+    for (int d = 0; d < 3; ++d) {
+      dims[d] = (int)std::floor(ext[d] / cell) + 1;
+      tot *= dims[d];
+    }
+    if (tot <= kMaxCells) break;
+    cell *= std::cbrt((double)tot / (double)kMaxCells) * 1.02;
+  }
+  GridDev& g = G.v;
+  g.ox = G.lo[0];
+  g.oy = G.lo[1];
+  g.oz = G.lo[2];
+  g.c = (float)cell;
+  g.inv_c = 1.0f / g.c;
+  g.dx = dims[0];
+  g.dy = dims[1];
+  g.dz = dims[2];
+  g.cdx = (g.dx + kCoarse - 1) >> kCoarseShift;
+  g.cdy = (g.dy + kCoarse - 1) >> kCoarseShift;
+  g.cdz = (g.dz + kCoarse - 1) >> kCoarseShift;
+  g.n = nfinite;
+  G.ncell = (int64_t)g.dx * g.dy * g.dz;
+  const int64_t ncoarse = (int64_t)g.cdx * g.cdy * g.cdz;
+  // 3. keys + histograms
+  G.cell_start.ensure((size_t)(G.ncell + 2) * 4);
+  G.coarse_cnt.ensure((size_t)ncoarse * 4);
+  G.pts.ensure((size_t)n * 16 + 16);
+  if (nrm) G.nrm.ensure((size_t)n * 16 + 16);
+  uint32_t* cell_start = G.cell_start.as<uint32_t>();
+  LC3D_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(G.ncell + 2) * 4, st));
+  LC3D_CUDA(cudaMemsetAsync(G.coarse_cnt.p, 0, (size_t)ncoarse * 4, st));
+  ctx->scratch[kScrKeys].ensure((size_t)n * 4);
+  ctx->scratch[kScrVals].ensure((size_t)n * 4);
+  ctx->scratch[kScrKeysAlt].ensure((size_t)n * 4);
+  ctx->scratch[kScrValsAlt].ensure((size_t)n * 4);
+  ctx->scratch[kScrHist].ensure(sort_hist_bytes(n));
+  ctx->scratch[kScrScan].ensure(
+      std::max(scan_scratch_bytes(G.ncell + 2), scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile))) + 64);
+  uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
+  uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
+  LC3D_LAUNCH(ctx, grid_keys, div_up(n, 256), 256, 0, xyz, n, g, (uint32_t)G.ncell, keys, vals,
+              cell_start, G.coarse_cnt.as<uint32_t>());
+  // 4. stable radix sort of (cell id, point index)
+  SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
+                 ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
+  radix_sort_pairs(ctx, keys, vals, n, bit_length((uint32_t)G.ncell), ss);
+  // 5. cell_start = exclusive scan of the cell histogram (ncell+1 entries)
+  exclusive_scan_u32(ctx, cell_start, cell_start, G.ncell + 1, ctx->scratch[kScrScan].as<uint32_t>());
+  // 6. gather into sorted SoA float4 (finite points come first: sentinel key sorts last)
+  LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, nrm, vals, n, G.pts.as<float4>(),
+              nrm ? G.nrm.as<float4>() : nullptr);
+  g.cell_start = cell_start;
+  g.coarse_cnt = G.coarse_cnt.as<uint32_t>();
+  g.pts = G.pts.as<float4>();
+  g.nrm = nrm ? G.nrm.as<float4>() : nullptr;
+}
+
+// Orders `xyz` (n float4) by the cell it falls into in grid g (clamped), for query
+// locality: queries consecutive in memory walk the same cell rows.  out[j].w = bits(orig idx).
+__global__ void __launch_bounds__(256)
+    query_keys(const float4* __restrict__ p, int n, GridDev g, uint32_t* __restrict__ keys,
+               uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = p[i];
+  uint32_t key = (uint32_t)g.dx * g.dy * g.dz;
+  if (finite3(q.x, q.y, q.z)) {
+    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
+    int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
+    int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
+    key = (uint32_t)((iz * g.dy + iy) * g.dx + ix);
+  }
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+}
+
+inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz, int64_t n64,
+                                 float4* out_sorted) {
+  const int n = (int)n64;
+  if (n == 0) return;
+  ctx->scratch[kScrKeys].ensure((size_t)n * 4);
+  ctx->scratch[kScrVals].ensure((size_t)n * 4);
+  ctx->scratch[kScrKeysAlt].ensure((size_t)n * 4);
+  ctx->scratch[kScrValsAlt].ensure((size_t)n * 4);
+  ctx->scratch[kScrHist].ensure(sort_hist_bytes(n));
+  ctx->scratch[kScrScan].ensure(scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile)) + 64);
+  uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
+  uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
+  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, keys, vals);
+  SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
+                 ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
+  radix_sort_pairs(ctx, keys, vals, n, bit_length((uint32_t)G.ncell), ss);
+  LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, (const float4*)nullptr, vals, n,
+              out_sorted, (float4*)nullptr);
+}
+
+}  // namespace lc3d

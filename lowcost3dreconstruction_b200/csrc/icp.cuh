@@ -1,0 +1,531 @@
+// icp.cuh — the ICP loop of pcl::IterativeClosestPoint::align as driven by
+// pcl_tools/fine_registration.cpp:105-126, entirely on the device.
+//
+// One kernel per iteration (icp_iteration_kernel) fuses
+//   transformCloud (incremental float32 transform of the source, applied at the head
+//     of the NEXT iteration because T_k is only known after the grid-wide reduce),
+//   determineCorrespondences (exact 1-NN + max-distance gate),
+//   the estimator's sums (3x3 cross-covariance for Umeyama/SVD, or the 6x6 normal
+//     equations of point-to-plane LLS) accumulated in fp64: warp shuffles -> shared
+//     memory -> per-block partials -> the last block to finish reduces them in a fixed
+//     order (deterministic), solves (3x3 one-sided Jacobi SVD / 6x6 elimination),
+//     composes final_transformation_ and runs DefaultConvergenceCriteria.
+// The host enqueues max_iterations launches back to back; once the device-side state
+// machine sets `done` the remaining launches return immediately.  No per-iteration
+// host round trip.
+#pragma once
+#include "search.cuh"
+
+namespace lc3d {
+
+constexpr int kIcpThreads = 256;
+constexpr int kNvP2P = 17;     // sum s(3) sum d(3) sum d s^T(9) sum d2(1) count(1)
+constexpr int kNvP2Plane = 29; // JtJ upper(21) Jtr(6) sum d2(1) count(1)
+
+struct IcpState {
+  float T[16];       // transformation_ of the last solve (row-major)
+  float Tfinal[16];  // final_transformation_
+  double prev_mse;   // correspondences_prev_mse_
+  double last_mse;
+  double fitness_sum;
+  long long fitness_cnt;
+  long long last_corr;
+  int iter;       // nr_iterations_
+  int done;       // loop finished
+  int converged;  // converged_
+  int state;      // LC3D_STATE_*
+  unsigned ticket;
+  unsigned ticket2;
+  int pad[2];
+};
+
+struct IcpConfig {
+  float gate;         // largest float <= max_correspondence_distance^2
+  int max_iterations;
+  double rot_thr;     // 1 - transformation_epsilon
+  double transl_thr;  // transformation_epsilon (squared translation)
+  double rel_mse;     // euclidean_fitness_epsilon
+  double abs_mse;     // 1e-12
+  int dump_iteration;
+  int mode;
+};
+
+__global__ void icp_state_init(IcpState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) st->T[i] = st->Tfinal[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    st->prev_mse = 1.7976931348623157e308;  // DBL_MAX
+    st->last_mse = 0.0;
+    st->fitness_sum = 0.0;
+    st->fitness_cnt = 0;
+    st->last_corr = 0;
+    st->iter = 0;
+    st->done = 0;
+    st->converged = 0;
+    st->state = LC3D_STATE_NOT_CONVERGED;
+    st->ticket = 0;
+    st->ticket2 = 0;
+  }
+}
+
+// ---- small dense solvers (fp64, single thread) --------------------------------------
+
+// Rotation of the Umeyama / Kabsch problem for cross-covariance S (row-major 3x3):
+// S = U D V^T, R = U diag(1,1,det(U)det(V)) V^T.  One-sided (Hestenes) Jacobi on the
+// columns of S; the third left vector is u1 x u2, which folds det(U) into the product.
+__device__ void kabsch_rotation_dev(const double* S, double* R) {
+  double A[9], V[9];
+  for (int i = 0; i < 9; ++i) {
+    A[i] = S[i];
+    V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double al = 0, be = 0, ga = 0;
+        for (int k = 0; k < 3; ++k) {
+          al += A[k * 3 + p] * A[k * 3 + p];
+          be += A[k * 3 + q] * A[k * 3 + q];
+          ga += A[k * 3 + p] * A[k * 3 + q];
+        }
+        if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+        rotated = true;
+        double zeta = (be - al) / (2.0 * ga);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < 3; ++k) {
+          double ap = A[k * 3 + p], aq = A[k * 3 + q];
+          A[k * 3 + p] = c * ap - s * aq;
+          A[k * 3 + q] = s * ap + c * aq;
+          double vp = V[k * 3 + p], vq = V[k * 3 + q];
+          V[k * 3 + p] = c * vp - s * vq;
+          V[k * 3 + q] = s * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double sg[3];
+  for (int c = 0; c < 3; ++c)
+    sg[c] = A[c] * A[c] + A[3 + c] * A[3 + c] + A[6 + c] * A[6 + c];
+  int o0 = 0, o1 = 1, o2 = 2;  // descending singular values
+  if (sg[o0] < sg[o1]) { int t = o0; o0 = o1; o1 = t; }
+  if (sg[o1] < sg[o2]) { int t = o1; o1 = o2; o2 = t; }
+  if (sg[o0] < sg[o1]) { int t = o0; o0 = o1; o1 = t; }
+  double U[9], W[9];
+  const int ord[3] = {o0, o1, o2};
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) W[r * 3 + c] = V[r * 3 + ord[c]];
+  for (int c = 0; c < 2; ++c) {
+    double nrm = sqrt(sg[ord[c]]);
+    for (int r = 0; r < 3; ++r) U[r * 3 + c] = nrm > 0 ? A[r * 3 + ord[c]] / nrm : (r == c ? 1.0 : 0.0);
+  }
+  {
+    double dot = U[0] * U[1] + U[3] * U[4] + U[6] * U[7], nrm = 0;
+    for (int r = 0; r < 3; ++r) {
+      U[r * 3 + 1] -= dot * U[r * 3 + 0];
+      nrm += U[r * 3 + 1] * U[r * 3 + 1];
+    }
+    nrm = sqrt(nrm);
+    if (nrm > 0)
+      for (int r = 0; r < 3; ++r) U[r * 3 + 1] /= nrm;
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+  double detW = W[0] * (W[4] * W[8] - W[5] * W[7]) - W[1] * (W[3] * W[8] - W[5] * W[6]) +
+                W[2] * (W[3] * W[7] - W[4] * W[6]);
+  double dv = detW < 0 ? -1.0 : 1.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      R[i * 3 + j] = U[i * 3 + 0] * W[j * 3 + 0] + U[i * 3 + 1] * W[j * 3 + 1] +
+                     dv * U[i * 3 + 2] * W[j * 3 + 2];
+}
+
+__device__ bool solve6_dev(double* A, double* b, double* x) {
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(A[r * 6 + c]) > fabs(A[piv * 6 + c])) piv = r;
+    if (A[piv * 6 + c] == 0.0) return false;
+    if (piv != c) {
+      for (int k = 0; k < 6; ++k) {
+        double t = A[c * 6 + k];
+        A[c * 6 + k] = A[piv * 6 + k];
+        A[piv * 6 + k] = t;
+      }
+      double t = b[c];
+      b[c] = b[piv];
+      b[piv] = t;
+    }
+    for (int r = c + 1; r < 6; ++r) {
+      double f = A[r * 6 + c] / A[c * 6 + c];
+      for (int k = c; k < 6; ++k) A[r * 6 + k] -= f * A[c * 6 + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < 6; ++k) s -= A[r * 6 + k] * x[k];
+    x[r] = s / A[r * 6 + r];
+  }
+  return true;
+}
+
+// Estimator + pose composition + DefaultConvergenceCriteria; run by
+// one thread of the last block.  v = the NV reduced sums.
+template <int MODE>
+__device__ void icp_solve_and_test(IcpState* st, const IcpConfig& cfg, const double* v) {
+  constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  const double cnt = v[NV - 1];
+  st->last_corr = (long long)cnt;
+  st->last_mse = cnt > 0 ? v[NV - 2] / cnt : 0.0;
+  if (cnt < 3.0) {  // "Not enough correspondences found"
+    st->state = LC3D_STATE_NO_CORRESPONDENCES;
+    st->converged = 0;
+    st->done = 1;
+    return;
+  }
+  float T[16];
+  for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  if (MODE == LC3D_ICP_POINT_TO_PLANE) {
+    double A[36], b[6], x[6];
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) {
+        A[i * 6 + j] = v[k];
+        A[j * 6 + i] = v[k];
+        ++k;
+      }
+    for (int i = 0; i < 6; ++i) b[i] = v[21 + i];
+    if (solve6_dev(A, b, x)) {
+      double al = x[0], be = x[1], ga = x[2];
+      double sa, ca, sb, cb, sg, cg;
+      sincos(al, &sa, &ca);
+      sincos(be, &sb, &cb);
+      sincos(ga, &sg, &cg);
+      T[0] = (float)(cg * cb);
+      T[1] = (float)(-sg * ca + cg * sb * sa);
+      T[2] = (float)(sg * sa + cg * sb * ca);
+      T[4] = (float)(sg * cb);
+      T[5] = (float)(cg * ca + sg * sb * sa);
+      T[6] = (float)(-cg * sa + sg * sb * ca);
+      T[8] = (float)(-sb);
+      T[9] = (float)(cb * sa);
+      T[10] = (float)(cb * ca);
+      T[3] = (float)x[3];
+      T[7] = (float)x[4];
+      T[11] = (float)x[5];
+    }
+  } else {
+    double mu_s[3], mu_d[3], S[9], R[9];
+    for (int k = 0; k < 3; ++k) {
+      mu_s[k] = v[k] / cnt;
+      mu_d[k] = v[3 + k] / cnt;
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) S[i * 3 + j] = v[6 + i * 3 + j] / cnt - mu_d[i] * mu_s[j];
+    kabsch_rotation_dev(S, R);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) T[i * 4 + j] = (float)R[i * 3 + j];
+      T[i * 4 + 3] =
+          (float)(mu_d[i] - (R[i * 3 + 0] * mu_s[0] + R[i * 3 + 1] * mu_s[1] + R[i * 3 + 2] * mu_s[2]));
+    }
+  }
+  // final_transformation_ = transformation_ * final_transformation_ (Matrix4f, float32)
+  float F[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float s = __fmul_rn(T[i * 4 + 0], st->Tfinal[0 * 4 + j]);
+      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 1], st->Tfinal[1 * 4 + j]));
+      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 2], st->Tfinal[2 * 4 + j]));
+      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 3], st->Tfinal[3 * 4 + j]));
+      F[i * 4 + j] = s;
+    }
+  for (int i = 0; i < 16; ++i) {
+    st->T[i] = T[i];
+    st->Tfinal[i] = F[i];
+  }
+  const int iter = st->iter + 1;
+  st->iter = iter;
+  // DefaultConvergenceCriteria::hasConverged
+  int state = LC3D_STATE_NOT_CONVERGED;
+  if (iter >= cfg.max_iterations) {
+    state = LC3D_STATE_ITERATIONS;
+  } else {
+    float tr = __fsub_rn(__fadd_rn(__fadd_rn(T[0], T[5]), T[10]), 1.0f);
+    double cos_angle = 0.5 * (double)tr;
+    double tsq = (double)__fmul_rn(T[3], T[3]) + (double)__fmul_rn(T[7], T[7]) +
+                 (double)__fmul_rn(T[11], T[11]);
+    if (cos_angle >= cfg.rot_thr && tsq <= cfg.transl_thr) {
+      state = LC3D_STATE_TRANSFORM;
+    } else {
+      double mse = st->last_mse;
+      if (fabs(mse - st->prev_mse) < cfg.abs_mse)
+        state = LC3D_STATE_ABS_MSE;
+      else if (fabs(mse - st->prev_mse) / st->prev_mse < cfg.rel_mse)
+        state = LC3D_STATE_REL_MSE;
+      else
+        st->prev_mse = mse;
+    }
+  }
+  st->state = state;
+  if (state != LC3D_STATE_NOT_CONVERGED) {
+    st->converged = 1;
+    st->done = 1;
+  }
+}
+
+// Deterministic grid-wide reduce of per-block partials by the last block, NV values.
+// partials layout: [v * nblk + b].  Warp w reduces values w, w+8, ...; lanes stride over
+// blocks in a fixed order, then a fixed-shape shuffle tree.
+template <int NV>
+__device__ __forceinline__ void last_block_reduce(const double* __restrict__ partials, int nblk,
+                                                  double* out_smem) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  for (int v = w; v < NV; v += nwarps) {
+    const volatile double* row = partials + (size_t)v * nblk;
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += row[b];
+    s = warp_sum(s);
+    if (lane == 0) out_smem[v] = s;
+  }
+}
+
+// One ICP iteration.  X: working copy of the source (float4, cell-sorted order, w =
+// original index), transformed in place.  One thread per source point.
+template <int MODE>
+__global__ void __launch_bounds__(kIcpThreads)
+    icp_iteration_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const GridDev g,
+                         float4* __restrict__ X, int n, double* __restrict__ partials,
+                         int32_t* __restrict__ dump_idx, float* __restrict__ dump_d2) {
+  constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  __shared__ double warp_part[kIcpThreads / 32][NV];
+  __shared__ double red[NV];
+  __shared__ float sT[16];
+  __shared__ int s_flags[2];
+  if (threadIdx.x == 0) {
+    s_flags[0] = st->done;
+    s_flags[1] = st->iter;
+  }
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+  __syncthreads();
+  if (s_flags[0]) return;
+  const int iter = s_flags[1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = i < n;
+  float4 q = active ? X[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  active = active && finite3(q.x, q.y, q.z);
+  if (active && iter > 0) {  // transformCloud with the previous iteration's T
+    float x = xform_row(sT, 0, q.x, q.y, q.z);
+    float y = xform_row(sT, 1, q.x, q.y, q.z);
+    float z = xform_row(sT, 2, q.x, q.y, q.z);
+    q.x = x;
+    q.y = y;
+    q.z = z;
+    X[i] = q;
+  }
+  Best b = nn_search(g, active, q.x, q.y, q.z, cfg.gate);
+  const bool has = active && b.j >= 0;
+  if (dump_idx && iter == cfg.dump_iteration && i < n) {
+    const int oi = __float_as_int(q.w);
+    dump_idx[oi] = has ? b.oi : -1;
+    dump_d2[oi] = has ? b.d2 : INFINITY;
+  }
+  // ---- estimator sums, fp64 ------------------------------------------------------
+  const unsigned any = __ballot_sync(0xffffffffu, has);
+  if (any) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has) d = __ldg(&g.pts[b.j]);
+    if (MODE == LC3D_ICP_POINT_TO_PLANE) {
+      double J[6] = {0, 0, 0, 0, 0, 0}, r = 0;
+      if (has) {
+        const float4 nn = __ldg(&g.nrm[b.j]);
+        if (finite3(nn.x, nn.y, nn.z)) {
+          // float32 products widened to double, as TransformationEstimationPointToPlaneLLS
+          J[0] = (double)__fsub_rn(__fmul_rn(nn.z, q.y), __fmul_rn(nn.y, q.z));
+          J[1] = (double)__fsub_rn(__fmul_rn(nn.x, q.z), __fmul_rn(nn.z, q.x));
+          J[2] = (double)__fsub_rn(__fmul_rn(nn.y, q.x), __fmul_rn(nn.x, q.y));
+          J[3] = nn.x;
+          J[4] = nn.y;
+          J[5] = nn.z;
+          float rr = __fmul_rn(nn.x, d.x);
+          rr = __fadd_rn(rr, __fmul_rn(nn.y, d.y));
+          rr = __fadd_rn(rr, __fmul_rn(nn.z, d.z));
+          rr = __fsub_rn(rr, __fmul_rn(nn.x, q.x));
+          rr = __fsub_rn(rr, __fmul_rn(nn.y, q.y));
+          rr = __fsub_rn(rr, __fmul_rn(nn.z, q.z));
+          r = (double)rr;
+        }
+      }
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = a; c < 6; ++c) {
+          double s = warp_sum(J[a] * J[c]);
+          if (lane == 0) warp_part[w][k] = s;
+          ++k;
+        }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = warp_sum(J[a] * r);
+        if (lane == 0) warp_part[w][21 + a] = s;
+      }
+    } else {
+      const double sx = has ? (double)q.x : 0.0, sy = has ? (double)q.y : 0.0, sz = has ? (double)q.z : 0.0;
+      const double dx = d.x, dy = d.y, dz = d.z;
+      const double sv[3] = {sx, sy, sz}, dv[3] = {dx, dy, dz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double s = warp_sum(sv[a]);
+        if (lane == 0) warp_part[w][a] = s;
+        s = warp_sum(dv[a]);
+        if (lane == 0) warp_part[w][3 + a] = s;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double s = warp_sum(dv[a] * sv[c]);
+          if (lane == 0) warp_part[w][6 + a * 3 + c] = s;
+        }
+    }
+    double s = warp_sum(has ? (double)b.d2 : 0.0);
+    if (lane == 0) {
+      warp_part[w][NV - 2] = s;
+      warp_part[w][NV - 1] = (double)__popc(any);
+    }
+  } else if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) warp_part[w][k] = 0.0;
+  }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += warp_part[ww][threadIdx.x];
+    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = s;
+  }
+  // ---- last block: reduce, solve, test convergence ---------------------------------
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(nblk - 1)) return;
+  __threadfence();
+  last_block_reduce<NV>(partials, nblk, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ticket = 0;
+    icp_solve_and_test<MODE>(st, cfg, red);
+  }
+}
+
+// ---- getFitnessScore (fine_registration.cpp:126) --------------------------
+// transformPointCloud(*input_, tmp, final_transformation_) then the unbounded 1-NN of every
+// point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
+__global__ void __launch_bounds__(kIcpThreads)
+    icp_fitness_kernel(IcpState* __restrict__ st, const GridDev g, const float4* __restrict__ src0,
+                       int n, double* __restrict__ partials) {
+  __shared__ double wsum[kIcpThreads / 32], wcnt[kIcpThreads / 32];
+  __shared__ float sT[16];
+  __shared__ double red[2];
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->Tfinal[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = i < n;
+  float4 q = active ? src0[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  active = active && finite3(q.x, q.y, q.z);
+  const float x = xform_row(sT, 0, q.x, q.y, q.z);
+  const float y = xform_row(sT, 1, q.x, q.y, q.z);
+  const float z = xform_row(sT, 2, q.x, q.y, q.z);
+  Best b = nn_search(g, active, x, y, z, INFINITY);
+  const bool has = active && b.j >= 0;
+  double s = warp_sum(has ? (double)b.d2 : 0.0);
+  unsigned any = __ballot_sync(0xffffffffu, has);
+  if (lane == 0) {
+    wsum[w] = s;
+    wcnt[w] = (double)__popc(any);
+  }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int ww = 0; ww < kIcpThreads / 32; ++ww) t += threadIdx.x == 0 ? wsum[ww] : wcnt[ww];
+    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
+  }
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket2, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(nblk - 1)) return;
+  __threadfence();
+  last_block_reduce<2>(partials, nblk, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ticket2 = 0;
+    st->fitness_sum = red[0];
+    st->fitness_cnt = (long long)red[1];
+  }
+}
+
+// registered = transformCloud(*input_, final_transformation_) (fine_registration.cpp:121),
+// also serves lc3d_transform (pcl_tools/transform.cpp:84-90).  Input order, packed xyz out.
+__global__ void __launch_bounds__(256)
+    transform_kernel(const float* __restrict__ T16, const float4* __restrict__ xyz,
+                     const float4* __restrict__ nrm, int n, float* __restrict__ out_xyz,
+                     float* __restrict__ out_nrm) {
+  __shared__ float sT[16];
+  if (threadIdx.x < 16) sT[threadIdx.x] = T16[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = xyz[i];
+  float ox = p.x, oy = p.y, oz = p.z;
+  if (finite3(p.x, p.y, p.z)) {
+    ox = xform_row(sT, 0, p.x, p.y, p.z);
+    oy = xform_row(sT, 1, p.x, p.y, p.z);
+    oz = xform_row(sT, 2, p.x, p.y, p.z);
+  }
+  out_xyz[3 * (size_t)i + 0] = ox;
+  out_xyz[3 * (size_t)i + 1] = oy;
+  out_xyz[3 * (size_t)i + 2] = oz;
+  if (nrm && out_nrm) {
+    float4 m = nrm[i];
+    float nx = m.x, ny = m.y, nz = m.z;
+    if (finite3(m.x, m.y, m.z)) {
+      nx = rot_row(sT, 0, m.x, m.y, m.z);
+      ny = rot_row(sT, 1, m.x, m.y, m.z);
+      nz = rot_row(sT, 2, m.x, m.y, m.z);
+    }
+    out_nrm[3 * (size_t)i + 0] = nx;
+    out_nrm[3 * (size_t)i + 1] = ny;
+    out_nrm[3 * (size_t)i + 2] = nz;
+  }
+}
+
+// Plain batched 1-NN (lc3d_nn): queries in cell-sorted order, results scattered back to
+// the original query order.
+__global__ void __launch_bounds__(256)
+    nn_kernel(const GridDev g, const float4* __restrict__ q_sorted, int n, float gate,
+              int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = i < n;
+  float4 q = active ? q_sorted[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  active = active && finite3(q.x, q.y, q.z);
+  Best b = nn_search(g, active, q.x, q.y, q.z, gate);
+  if (i < n) {
+    const int oi = __float_as_int(q.w);
+    const bool has = active && b.j >= 0;
+    out_idx[oi] = has ? b.oi : -1;
+    out_d2[oi] = has ? b.d2 : INFINITY;
+  }
+}
+
+}  // namespace lc3d

@@ -1,0 +1,239 @@
+// scan_sort.cuh — hand-written exclusive scan and stable LSD radix sort (key32 + value32).
+//
+// These build the spatial index (cell-id keys) and the VoxelGrid ordering.  No CUB /
+// Thrust: the north star asks for a hand-written sort.  Both are HBM/L2 streaming
+// kernels: vectorised coalesced loads, shared-memory histograms, warp match ranking.
+#pragma once
+#include "common.cuh"
+
+namespace lc3d {
+
+// ------------------------------------------------------------------ scan -----
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  // exclusive scan of one value per thread across the block (kScanThreads threads)
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  __shared__ uint32_t block_tot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = lane < kScanThreads / 32 ? warp_tot[lane] : 0u;
+    uint32_t ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    if (lane < kScanThreads / 32) warp_tot[lane] = ti - t;
+    if (lane == 31) block_tot = ti;
+  }
+  __syncthreads();
+  uint32_t r = inc - v + warp_tot[w];
+  *total = block_tot;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in,
+                                                               int64_t n,
+                                                               uint32_t* __restrict__ sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+  if (base + kScanItems <= n) {
+    const uint4* p = reinterpret_cast<const uint4*>(in + base);
+    uint4 a = p[0], b = p[1];
+    s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) s += in[base + k];
+  }
+  uint32_t tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums(uint32_t* sums, int nb) {
+  // single block: exclusive scan of the tile sums, chunked with a running carry
+  uint32_t carry = 0;
+  for (int base = 0; base < nb; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nb ? sums[i] : 0u;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(v, &tot);
+    if (i < nb) sums[i] = ex + carry;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in,
+                                                           uint32_t* __restrict__ out, int64_t n,
+                                                           const uint32_t* __restrict__ sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  const bool full = base + kScanItems <= n;
+  if (full) {
+    const uint4* p = reinterpret_cast<const uint4*>(in + base);
+    uint4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = base + k < n ? in[base + k] : 0u;
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) s += v[k];
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan(s, &tot) + sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    uint32_t t = v[k];
+    v[k] = ex;
+    ex += t;
+  }
+  if (full) {
+    uint4* p = reinterpret_cast<uint4*>(out + base);
+    p[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    p[1] = make_uint4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) out[base + k] = v[k];
+  }
+}
+
+// Exclusive scan of n uint32 (in may alias out).  `sums` scratch: >= div_up(n, kScanTile) u32.
+// Requires in/out 16-byte aligned (cudaMalloc'd).
+inline void exclusive_scan_u32(lc3d_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
+                               uint32_t* sums) {
+  if (n <= 0) return;
+  int nb = div_up(n, kScanTile);
+  LC3D_LAUNCH(ctx, scan_tile_sums, nb, kScanThreads, 0, in, n, sums);
+  LC3D_LAUNCH(ctx, scan_block_sums, 1, kScanThreads, 0, sums, nb);
+  LC3D_LAUNCH(ctx, scan_apply, nb, kScanThreads, 0, in, out, n, sums);
+}
+inline size_t scan_scratch_bytes(int64_t n) { return (size_t)(div_up(n, kScanTile) + 1) * 4; }
+
+// ------------------------------------------------------------ radix sort -----
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortRounds = 8;                       // keys per thread
+constexpr int kSortTile = kSortThreads * kSortRounds;  // 2048 keys per block
+constexpr int kRadix = 256;
+
+// hist[d * nblk + b] = number of keys of block b with digit d
+__global__ void __launch_bounds__(kSortThreads) radix_hist(const uint32_t* __restrict__ keys,
+                                                           int64_t n, int shift, int nblk,
+                                                           uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kRadix];
+  for (int i = threadIdx.x; i < kRadix; i += kSortThreads) h[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    int64_t i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRadix; i += kSortThreads) hist[(size_t)i * nblk + blockIdx.x] = h[i];
+}
+
+// Stable scatter.  Warp w of block b owns the contiguous keys
+// [b*tile + w*256, b*tile + (w+1)*256), processed as 8 rounds of 32 consecutive keys;
+// __match_any_sync ranks equal digits inside a round in lane (= input) order.
+__global__ void __launch_bounds__(kSortThreads)
+    radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                  int shift, int nblk, const uint32_t* __restrict__ hist_scanned) {
+  __shared__ uint32_t cnt[kSortWarps][kRadix + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kSortWarps * (kRadix + 1); i += kSortThreads)
+    (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortRounds * 32);
+  uint32_t key[kSortRounds], val[kSortRounds], rank[kSortRounds];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    int64_t i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    key[r] = ok ? keys_in[i] : 0xffffffffu;
+    val[r] = ok ? vals_in[i] : 0u;
+    uint32_t d = ok ? ((key[r] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t prev = cnt[w][d];
+    __syncwarp();
+    if ((peers & lt) == 0) cnt[w][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + __popc(peers & lt);
+  }
+  __syncthreads();
+  // per-digit exclusive prefix over the warps of this block (thread d handles digit d)
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
+    uint32_t run = hist_scanned[(size_t)d * nblk + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < kSortWarps; ++ww) {
+      uint32_t c = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    int64_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      uint32_t d = (key[r] >> shift) & (kRadix - 1);
+      uint32_t dst = cnt[w][d] + rank[r];
+      keys_out[dst] = key[r];
+      vals_out[dst] = val[r];
+    }
+  }
+}
+
+// NOTE: radix_hist above indexes keys block-strided, the scatter warp-contiguous; both
+// cover exactly the same tile [b*tile, (b+1)*tile), so per-block digit counts agree.
+
+struct SortScratch {
+  uint32_t* keys_alt;
+  uint32_t* vals_alt;
+  uint32_t* hist;      // kRadix * nblk (+ scan sums appended)
+  uint32_t* scan_sums;
+};
+inline size_t sort_hist_bytes(int64_t n) { return (size_t)kRadix * div_up(n, kSortTile) * 4 + 64; }
+
+// Sorts (keys, vals) ascending by the low `bits` bits of key, stable.  On return the
+// sorted data are in (keys, vals) (the function copies back if the pass count is odd).
+inline void radix_sort_pairs(lc3d_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits,
+                             const SortScratch& s) {
+  if (n <= 1) return;
+  int passes = (bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  int nblk = div_up(n, kSortTile);
+  uint32_t *kin = keys, *vin = vals, *kout = s.keys_alt, *vout = s.vals_alt;
+  for (int p = 0; p < passes; ++p) {
+    int shift = p * 8;
+    LC3D_LAUNCH(ctx, radix_hist, nblk, kSortThreads, 0, kin, n, shift, nblk, s.hist);
+    exclusive_scan_u32(ctx, s.hist, s.hist, (int64_t)kRadix * nblk, s.scan_sums);
+    LC3D_LAUNCH(ctx, radix_scatter, nblk, kSortThreads, 0, kin, vin, kout, vout, n, shift, nblk,
+                s.hist);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  if (kin != keys) {
+    LC3D_CUDA(cudaMemcpyAsync(keys, kin, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    LC3D_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+}
+
+}  // namespace lc3d
