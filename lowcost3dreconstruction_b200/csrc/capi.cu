@@ -413,6 +413,6 @@ int lc3d_transform(lc3d_ctx* ctx, const lc3d_cloud* cloud, const float matrix[16
   });
 }
 
-#include "capi_filters.inc"
-
 }  // extern "C"
+
+#include "capi_filters.inc"

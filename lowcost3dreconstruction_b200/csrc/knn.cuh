@@ -1,3 +1,481 @@
-// knn.cuh — placeholder, filled in below.
+// knn.cuh — exact k-nearest-neighbour search on the uniform grid, one warp per query, and
+// the two consumers the reference feeds with it:
+//   * pcl::StatisticalOutlierRemoval (outlier_removal.cpp:80-84): mean distance
+//     to the k nearest neighbours,
+//   * pcl::NormalEstimation (normal_estimation.cpp:84-108): float32 single-pass
+//     covariance -> closed-form smallest eigenpair (pcl::eigen33) -> viewpoint flip.
+//
+// Search: the warp walks Chebyshev rings of cells around the query (x-runs of cells are
+// contiguous point ranges), lanes stride over the points of a run, candidates whose key
+// (d2 bits << 32 | original index) beats the running k-th key are appended to a per-warp
+// shared-memory buffer with ballot/popc; when the buffer fills, and after every ring, it
+// is bitonic-sorted and truncated to k.  The search stops when the k-th distance is within
+// the guaranteed radius of the scanned block, which makes the result exact; order is
+// ascending (d2, index) — the order PCL's consumers sum in.
 #pragma once
 #include "search.cuh"
+
+namespace lc3d {
+
+constexpr int kKnnWarps = 4;  // warps (= queries in flight) per block
+constexpr unsigned long long kMaxKey = 0xffffffffffffffffull;
+
+template <int CAP>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* buf, int lane) {
+  for (int kk = 2; kk <= CAP; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = lane; t < CAP / 2; t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool asc = (i & kk) == 0;
+        const unsigned long long a = buf[i], b = buf[l];
+        if ((a > b) == asc) {
+          buf[i] = b;
+          buf[l] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int CAP>
+struct KnnState {
+  unsigned long long* buf;  // CAP keys, per warp, shared memory
+  int cnt;                  // valid keys in buf (warp-uniform)
+  unsigned long long thresh;  // keys >= thresh cannot enter the top-k (warp-uniform)
+  int k;
+};
+
+template <int CAP>
+__device__ __forceinline__ void knn_sort_truncate(KnnState<CAP>& s, int lane) {
+  for (int t = s.cnt + lane; t < CAP; t += 32) s.buf[t] = kMaxKey;
+  __syncwarp();
+  warp_bitonic_sort<CAP>(s.buf, lane);
+  if (s.cnt > s.k) s.cnt = s.k;
+  s.thresh = s.cnt == s.k ? s.buf[s.k - 1] : kMaxKey;
+}
+
+// Lanes stride over the points [s0, e0) of one cell run.
+template <int CAP>
+__device__ __forceinline__ void knn_scan_run(const float4* __restrict__ pts, uint32_t s0, uint32_t e0,
+                                             float qx, float qy, float qz, KnnState<CAP>& s, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  for (uint32_t j0 = s0; j0 < e0; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    bool pass = false;
+    unsigned long long key = 0;
+    if (j < e0) {
+      const float4 p = __ldg(&pts[j]);
+      const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+      pass = key < s.thresh;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) s.buf[s.cnt + __popc(m & lt)] = key;
+    s.cnt += __popc(m);
+    __syncwarp();
+    if (s.cnt > CAP - 32) knn_sort_truncate<CAP>(s, lane);
+  }
+}
+
+// Exact kNN of (qx,qy,qz); on return s.buf[0..s.cnt) holds the neighbours ascending.
+// Warp-uniform.  k <= CAP - 32.
+template <int CAP>
+__device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, KnnState<CAP>& s,
+                                int lane) {
+  s.cnt = 0;
+  s.thresh = kMaxKey;
+  if (g.n == 0) return;
+  const QueryCell qc = query_cell(g, qx, qy, qz);
+  const float c2 = g.c * g.c * 0.9999f;
+  // first ring that touches the grid (queries may lie outside it)
+  int K = 0;
+  K = max(K, max(-qc.ix, qc.ix - (g.dx - 1)));
+  K = max(K, max(-qc.iy, qc.iy - (g.dy - 1)));
+  K = max(K, max(-qc.iz, qc.iz - (g.dz - 1)));
+  // with ~cell_factor^2 points per occupied cell, ring K holds ~pi K^2 cf^2 points within
+  // its guaranteed radius: jump to the first ring that can hold k (all inner rings are
+  // scanned as part of the first block)
+  int Kfirst = max(K, (int)ceilf(sqrtf((float)s.k * (1.0f / 12.0f))));
+  bool first = true;
+  for (;; ++K) {
+    if (first) K = Kfirst;
+    const float thr_d2 = __uint_as_float((unsigned)(s.thresh >> 32));  // k-th best d2 (or NaN bits)
+    const bool have_thr = s.thresh != kMaxKey;
+    const int y0 = max(qc.iy - K, 0), y1 = min(qc.iy + K, g.dy - 1);
+    const int z0 = max(qc.iz - K, 0), z1 = min(qc.iz + K, g.dz - 1);
+    const int xa = max(qc.ix - K, 0), xb = min(qc.ix + K, g.dx - 1);
+    for (int zz = z0; zz <= z1; ++zz) {
+      const float gz = slab_gap(qc.fz, zz, zz);
+      for (int yy = y0; yy <= y1; ++yy) {
+        const float gy = slab_gap(qc.fy, yy, yy);
+        if (have_thr && (gy * gy + gz * gz) * c2 > thr_d2) continue;
+        const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+        const bool outer = first || max(abs(yy - qc.iy), abs(zz - qc.iz)) == K;
+        if (outer) {
+          if (xa <= xb) knn_scan_run<CAP>(g.pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, s, lane);
+        } else {
+          const int xl = qc.ix - K, xh = qc.ix + K;
+          if (xl >= 0 && xl < g.dx)
+            knn_scan_run<CAP>(g.pts, __ldg(row + xl), __ldg(row + xl + 1), qx, qy, qz, s, lane);
+          if (xh >= 0 && xh < g.dx)
+            knn_scan_run<CAP>(g.pts, __ldg(row + xh), __ldg(row + xh + 1), qx, qy, qz, s, lane);
+        }
+      }
+    }
+    first = false;
+    knn_sort_truncate<CAP>(s, lane);
+    // guaranteed radius of the scanned block (faces with no grid behind them bound nothing)
+    float gmin = 1.0e30f;
+    bool open = false;
+    if (qc.ix - K > 0) { gmin = fminf(gmin, qc.fx - (float)(qc.ix - K)); open = true; }
+    if (qc.ix + K + 1 < g.dx) { gmin = fminf(gmin, (float)(qc.ix + K + 1) - qc.fx); open = true; }
+    if (qc.iy - K > 0) { gmin = fminf(gmin, qc.fy - (float)(qc.iy - K)); open = true; }
+    if (qc.iy + K + 1 < g.dy) { gmin = fminf(gmin, (float)(qc.iy + K + 1) - qc.fy); open = true; }
+    if (qc.iz - K > 0) { gmin = fminf(gmin, qc.fz - (float)(qc.iz - K)); open = true; }
+    if (qc.iz + K + 1 < g.dz) { gmin = fminf(gmin, (float)(qc.iz + K + 1) - qc.fz); open = true; }
+    if (!open) break;
+    gmin = fmaxf(gmin - kCellSlack, 0.0f);
+    if (s.cnt == s.k) {
+      const float kd2 = __uint_as_float((unsigned)(s.buf[s.k - 1] >> 32));
+      if (kd2 <= gmin * gmin * c2) break;
+    }
+  }
+}
+
+// ---- pcl::eigen33 smallest eigenpair, float32, closed form.  This TU is
+// compiled with -fmad=false so the float expressions below evaluate as written.
+__device__ __forceinline__ void roots2_dev(float b, float c, float* r) {
+  r[0] = 0.0f;
+  float d = (float)((double)(b * b) - 4.0 * (double)c);
+  if (d < 0.0f) d = 0.0f;
+  float sd = sqrtf(d);
+  r[2] = 0.5f * (b + sd);
+  r[1] = 0.5f * (b - sd);
+}
+__device__ __forceinline__ void swapf(float& a, float& b) {
+  float t = a;
+  a = b;
+  b = t;
+}
+__device__ void roots3_dev(const float* m, float* r) {
+  float c0 = m[0] * m[4] * m[8] + 2.0f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] -
+             m[8] * m[1] * m[1];
+  float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  float c2 = m[0] + m[4] + m[8];
+  if (fabsf(c0) < 1.1920929e-07f) {  // FLT_EPSILON
+    roots2_dev(c2, c1, r);
+    return;
+  }
+  const float inv3 = (float)(1.0 / 3.0);
+  const float sqrt3 = sqrtf(3.0f);
+  float c2_3 = c2 * inv3;
+  float a_3 = (c1 - c2 * c2_3) * inv3;
+  if (a_3 > 0.0f) a_3 = 0.0f;
+  float half_b = 0.5f * (c0 + c2_3 * (2.0f * c2_3 * c2_3 - c1));
+  float q = half_b * half_b + a_3 * a_3 * a_3;
+  if (q > 0.0f) q = 0.0f;
+  float rho = sqrtf(-a_3);
+  float theta = atan2f(sqrtf(-q), half_b) * inv3;
+  float ct = cosf(theta), st = sinf(theta);
+  r[0] = c2_3 + 2.0f * rho * ct;
+  r[1] = c2_3 - rho * (ct + sqrt3 * st);
+  r[2] = c2_3 - rho * (ct - sqrt3 * st);
+  if (r[0] >= r[1]) swapf(r[0], r[1]);
+  if (r[1] >= r[2]) {
+    swapf(r[1], r[2]);
+    if (r[0] >= r[1]) swapf(r[0], r[1]);
+  }
+  if (r[0] <= 0.0f) roots2_dev(c2, c1, r);
+}
+__device__ __forceinline__ void cross3_dev(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ void eigen33_smallest_dev(const float* C, float* eigenvalue, float* v) {
+  float scale = 0.0f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(C[i]));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;  // FLT_MIN
+  float m[9];
+  for (int i = 0; i < 9; ++i) m[i] = C[i] / scale;
+  float r[3];
+  roots3_dev(m, r);
+  *eigenvalue = r[0] * scale;
+  m[0] -= r[0];
+  m[4] -= r[0];
+  m[8] -= r[0];
+  float v1[3], v2[3], v3[3];
+  cross3_dev(&m[0], &m[3], v1);
+  cross3_dev(&m[0], &m[6], v2);
+  cross3_dev(&m[3], &m[6], v3);
+  float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float* best;
+  float len;
+  if (l1 >= l2 && l1 >= l3) {
+    best = v1;
+    len = l1;
+  } else if (l2 >= l1 && l2 >= l3) {
+    best = v2;
+    len = l2;
+  } else {
+    best = v3;
+    len = l3;
+  }
+  float s = sqrtf(len);
+  for (int k = 0; k < 3; ++k) v[k] = best[k] / s;
+}
+
+enum KnnConsumer { kConsumeIndices = 0, kConsumeSor = 1, kConsumeNormals = 2 };
+
+struct KnnArgs {
+  const float4* queries;  // cell-sorted order, w = original query index
+  int nq;
+  int k;
+  const float4* xyz_in;  // cloud in input order (normals consumer gathers neighbours here)
+  // outputs (indexed by original query index)
+  int32_t* out_idx;   // nq x k   (kConsumeIndices)
+  float* out_d2;      // nq x k
+  float* out_mean;    // nq       (kConsumeSor): mean distance, 0 for invalid
+  uint8_t* out_valid; // nq       (kConsumeSor)
+  float* out_normal;  // nq x 3   (kConsumeNormals)
+  float* out_curv;    // nq
+  float vpx, vpy, vpz;
+};
+
+template <int CAP, int CONSUMER>
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const GridDev g, const KnnArgs a) {
+  __shared__ unsigned long long sbuf[kKnnWarps][CAP];
+  __shared__ float snb[CONSUMER == kConsumeNormals ? kKnnWarps : 1][CONSUMER == kConsumeNormals ? CAP : 1][3];
+  __shared__ double sdist[CONSUMER == kConsumeSor ? kKnnWarps : 1][CONSUMER == kConsumeSor ? CAP : 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int qi = blockIdx.x * kKnnWarps + w;
+  if (qi >= a.nq) return;
+  const float4 q = a.queries[qi];
+  const int oq = __float_as_int(q.w);
+  KnnState<CAP> s;
+  s.buf = sbuf[w];
+  s.k = a.k;
+  s.cnt = 0;
+  s.thresh = kMaxKey;
+  const bool ok = finite3(q.x, q.y, q.z);
+  if (ok) knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane);
+  __syncwarp();
+  if (CONSUMER == kConsumeIndices) {
+    for (int t = lane; t < a.k; t += 32) {
+      const bool has = t < s.cnt;
+      const unsigned long long key = has ? s.buf[t] : 0ull;
+      a.out_idx[(size_t)oq * a.k + t] = has ? (int)(unsigned)(key & 0xffffffffu) : -1;
+      a.out_d2[(size_t)oq * a.k + t] = has ? __uint_as_float((unsigned)(key >> 32)) : INFINITY;
+    }
+  } else if (CONSUMER == kConsumeSor) {
+    // dist_sum = sum_{j=1..k-1} sqrt(d2_j) in double, ascending order (index 0 = the query
+    // itself); distances[i] = (float)(dist_sum / mean_k), mean_k = k - 1.
+    for (int t = lane; t < s.cnt; t += 32)
+      sdist[w][t] = sqrt((double)__uint_as_float((unsigned)(s.buf[t] >> 32)));
+    __syncwarp();
+    if (lane == 0) {
+      float md = 0.0f;
+      uint8_t valid = 0;
+      if (ok && s.cnt > 0) {
+        double sum = 0.0;
+        for (int t = 1; t < s.cnt; ++t) sum += sdist[w][t];
+        md = (float)(sum / (double)(a.k - 1));
+        valid = 1;
+      }
+      a.out_mean[oq] = md;
+      a.out_valid[oq] = valid;
+    }
+  } else {
+    // gather the neighbours' coordinates in parallel, then accumulate the 9 float32 sums of
+    // computeMeanAndCovarianceMatrix sequentially in neighbour order (lane a owns sum a)
+    for (int t = lane; t < s.cnt; t += 32) {
+      const float4 p = __ldg(&a.xyz_in[(unsigned)(s.buf[t] & 0xffffffffu)]);
+      snb[w][t][0] = p.x;
+      snb[w][t][1] = p.y;
+      snb[w][t][2] = p.z;
+    }
+    __syncwarp();
+    float acc = 0.0f;
+    if (lane < 9) {
+      // accu layout: xx xy xz yy yz zz x y z
+      const int ia = lane < 3 ? 0 : lane < 5 ? 1 : lane == 5 ? 2 : lane - 6;
+      const int ib = lane < 3 ? lane : lane < 5 ? lane - 2 : lane == 5 ? 2 : -1;
+      for (int t = 0; t < s.cnt; ++t) {
+        const float va = snb[w][t][ia];
+        const float term = ib >= 0 ? va * snb[w][t][ib] : va;
+        acc += term;
+      }
+      acc /= (float)s.cnt;
+    }
+    float accu[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) accu[i] = __shfl_sync(0xffffffffu, acc, i);
+    if (lane == 0) {
+      float nx, ny, nz, curv;
+      if (!ok || s.cnt < 3) {
+        nx = ny = nz = curv = __int_as_float(0x7fc00000);
+      } else {
+        float C[9];
+        C[0] = accu[0] - accu[6] * accu[6];
+        C[1] = accu[1] - accu[6] * accu[7];
+        C[2] = accu[2] - accu[6] * accu[8];
+        C[4] = accu[3] - accu[7] * accu[7];
+        C[5] = accu[4] - accu[7] * accu[8];
+        C[8] = accu[5] - accu[8] * accu[8];
+        C[3] = C[1];
+        C[6] = C[2];
+        C[7] = C[5];
+        float ev, v[3];
+        eigen33_smallest_dev(C, &ev, v);
+        const float tr = C[0] + C[4] + C[8];
+        curv = tr != 0.0f ? fabsf(ev / tr) : 0.0f;
+        const float vx = a.vpx - q.x, vy = a.vpy - q.y, vz = a.vpz - q.z;
+        const float cs = vx * v[0] + vy * v[1] + vz * v[2];
+        if (cs < 0.0f) {
+          v[0] *= -1.0f;
+          v[1] *= -1.0f;
+          v[2] *= -1.0f;
+        }
+        nx = v[0];
+        ny = v[1];
+        nz = v[2];
+      }
+      a.out_normal[3 * (size_t)oq + 0] = nx;
+      a.out_normal[3 * (size_t)oq + 1] = ny;
+      a.out_normal[3 * (size_t)oq + 2] = nz;
+      a.out_curv[oq] = curv;
+    }
+  }
+}
+
+template <int CONSUMER>
+inline void knn_launch(lc3d_ctx* ctx, const GridDev& g, const KnnArgs& a) {
+  if (a.nq == 0) return;
+  const int grid = div_up(a.nq, kKnnWarps);
+  if (a.k <= 32)
+    LC3D_LAUNCH(ctx, (knn_kernel<64, CONSUMER>), grid, kKnnWarps * 32, 0, g, a);
+  else if (a.k <= 96)
+    LC3D_LAUNCH(ctx, (knn_kernel<128, CONSUMER>), grid, kKnnWarps * 32, 0, g, a);
+  else if (a.k <= 224)
+    LC3D_LAUNCH(ctx, (knn_kernel<256, CONSUMER>), grid, kKnnWarps * 32, 0, g, a);
+  else if (a.k <= 480)
+    LC3D_LAUNCH(ctx, (knn_kernel<512, CONSUMER>), grid, kKnnWarps * 32, 0, g, a);
+  else
+    throw CudaError{"k too large (max 480)"};
+}
+
+// ---- SOR statistics + classification ------------------------------------
+struct SorStats {
+  double sum, sq_sum;
+  long long valid;
+  double mean, stddev, thr;
+  unsigned ticket;
+  unsigned pad;
+};
+
+__global__ void __launch_bounds__(256)
+    sor_stats_kernel(const float* __restrict__ dist, const uint8_t* __restrict__ valid, int n,
+                     double std_mul, double* __restrict__ partials, SorStats* __restrict__ st) {
+  __shared__ double ws[8][3];
+  __shared__ double red[3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double s = 0, sq = 0, c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (valid[i]) {
+      const float d = dist[i];
+      s += (double)d;
+      sq += (double)(d * d);  // float32 product, as PCL
+      c += 1.0;
+    }
+  }
+  s = warp_sum(s);
+  sq = warp_sum(sq);
+  c = warp_sum(c);
+  if (lane == 0) {
+    ws[w][0] = s;
+    ws[w][1] = sq;
+    ws[w][2] = c;
+  }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int ww = 0; ww < 8; ++ww) t += ws[ww][threadIdx.x];
+    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
+  }
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(nblk - 1)) return;
+  __threadfence();
+  {
+    for (int v = w; v < 3; v += 8) {
+      const volatile double* row = partials + (size_t)v * nblk;
+      double t = 0.0;
+      for (int b = lane; b < nblk; b += 32) t += row[b];
+      t = warp_sum(t);
+      if (lane == 0) red[v] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ticket = 0;
+    const double sum = red[0], sqs = red[1], nv = red[2];
+    st->sum = sum;
+    st->sq_sum = sqs;
+    st->valid = (long long)nv;
+    const double mean = sum / nv;
+    const double var = (sqs - sum * sum / nv) / (nv - 1.0);
+    const double sd = sqrt(var);
+    st->mean = mean;
+    st->stddev = sd;
+    st->thr = mean + std_mul * sd;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    sor_flag_kernel(const float* __restrict__ dist, int n, const SorStats* __restrict__ st, int negative,
+                    uint32_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool outlier = (double)dist[i] > st->thr;  // float vs double compare, as PCL
+  flags[i] = (negative ? outlier : !outlier) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+    compact_indices_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int n,
+                           int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i]) out[pos[i]] = i;
+}
+
+// pcl::compute3DCentroid: float32 sequential sum in input order / count.  Sequential by
+// definition (bit-parity with the float32 reference sum); one thread, L2-resident data.
+__global__ void centroid_kernel(const float4* __restrict__ xyz, int n, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    const float4 p = xyz[i];
+    if (!finite3(p.x, p.y, p.z)) continue;
+    sx += p.x;
+    sy += p.y;
+    sz += p.z;
+    ++cnt;
+  }
+  const float fc = (float)cnt;
+  out[0] = sx / fc;
+  out[1] = sy / fc;
+  out[2] = sz / fc;
+  out[3] = 1.0f;
+}
+
+}  // namespace lc3d

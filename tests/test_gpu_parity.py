@@ -1,0 +1,336 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north star): correspondence / neighbour index sets bit-exact (exact
+distance ties are resolved identically here: lower index), voxel / outlier masks bit-exact,
+final transforms within 1e-4 rad and 1e-5 x extent, fitness within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from lowcost3dreconstruction_b200 import api, synth
+from lowcost3dreconstruction_b200._capi import HostCloud
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4      # rad
+TRANS_TOL = 1e-5    # x cloud extent
+FIT_TOL = 1e-5      # relative
+
+
+def rot_angle(Ta, Tb):
+    """Relative rotation angle, from the antisymmetric part (arccos of the trace loses half
+    the digits near zero and float32 matrices are only orthonormal to ~1e-7)."""
+    R = Ta[:3, :3].astype(np.float64) @ Tb[:3, :3].astype(np.float64).T
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = float(np.linalg.norm(w))
+    c = (np.trace(R) - 1.0) / 2.0
+    return float(np.arctan2(s, c))
+
+
+def assert_transform_close(Tg, To, extent):
+    assert rot_angle(Tg, To) <= ROT_TOL
+    assert np.abs(Tg[:3, 3].astype(np.float64) - To[:3, 3]).max() <= TRANS_TOL * extent
+
+
+@pytest.fixture(scope="module")
+def pair():
+    tgt = synth.kinect_view(0, scale=0.4, backdrop="panel")
+    src = synth.kinect_view(1, scale=0.4, backdrop="panel")
+    return src, tgt
+
+
+@pytest.fixture(scope="module")
+def pair_normals(pair, ctx):
+    src, tgt = pair
+    n_t, c_t = orc.normals(tgt, 20)
+    n_s, c_s = orc.normals(src, 20)
+    return HostCloud(src, normal=n_s, curvature=c_s), HostCloud(tgt, normal=n_t, curvature=c_t)
+
+
+# ------------------------------------------------------------------ 1-NN / correspondences
+
+@pytest.mark.parametrize("max_dist", [0.0, 0.02, 0.004])
+def test_nn_bit_exact(ctx, pair, max_dist):
+    src, tgt = pair
+    oi, od = orc.KdTree(tgt).nn(src, max_dist)
+    gi, gd = api.nn(tgt, src, max_dist, ctx=ctx)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gd, od)  # float32 squared distances, bit for bit
+
+
+def test_nn_queries_far_outside_grid(ctx):
+    rng = np.random.default_rng(3)
+    tgt = rng.uniform(-1, 1, (5000, 3)).astype(np.float32)
+    q = np.concatenate([rng.uniform(-30, 30, (2000, 3)), rng.uniform(-1, 1, (500, 3))]).astype(np.float32)
+    oi, od = orc.KdTree(tgt).nn(q)
+    gi, gd = api.nn(tgt, q, ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_nn_degenerate_inputs(ctx):
+    one = np.array([[0.5, -1.0, 2.0]], dtype=np.float32)
+    q = np.array([[0, 0, 0], [1, 1, 1]], dtype=np.float32)
+    gi, gd = api.nn(one, q, ctx=ctx)
+    assert gi.tolist() == [0, 0]
+    # all-identical points: tie -> lowest index
+    same = np.tile(one, (100, 1))
+    gi, gd = api.nn(same, q, ctx=ctx)
+    assert gi.tolist() == [0, 0]
+    # duplicates + NaN points in the target are skipped
+    t = np.array([[0, 0, 0], [np.nan, 0, 0], [1, 1, 1], [1, 1, 1]], dtype=np.float32)
+    gi, gd = api.nn(t, q, ctx=ctx)
+    assert gi.tolist() == [0, 2]
+    # planar / collinear clouds (zero extent in some dimension)
+    rng = np.random.default_rng(0)
+    plane = rng.uniform(0, 1, (3000, 3)).astype(np.float32)
+    plane[:, 2] = 0.25
+    qq = rng.uniform(-0.5, 1.5, (1000, 3)).astype(np.float32)
+    oi, od = orc.KdTree(plane).nn(qq)
+    gi, gd = api.nn(plane, qq, ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_nn_volumetric_random(ctx):
+    rng = np.random.default_rng(11)
+    tgt = rng.normal(0, 1, (40000, 3)).astype(np.float32)
+    q = rng.normal(0, 1.3, (30000, 3)).astype(np.float32)
+    for md in (0.0, 0.05):
+        oi, od = orc.KdTree(tgt).nn(q, md)
+        gi, gd = api.nn(tgt, q, md, ctx=ctx)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+# ------------------------------------------------------------------------------- ICP
+
+@pytest.mark.parametrize("dump_it", [0, 4, 12])
+def test_icp_p2p_matches_oracle(ctx, pair, dump_it):
+    src, tgt = pair
+    extent = float(np.ptp(tgt, axis=0).max())
+    o = orc.icp_align(src, tgt, 0.02, 50, dump_iteration=dump_it, want_registered=True)
+    g = api.icp_align(src, tgt, 0.02, 50, dump_iteration=dump_it, want_registered=True, ctx=ctx)
+    assert g["iterations"] == o["iterations"] and g["state"] == o["state"] and g["converged"] == o["converged"]
+    assert_transform_close(g["transformation"], o["transformation"], extent)
+    assert abs(g["fitness"] - o["fitness"]) <= FIT_TOL * o["fitness"]
+    if dump_it < o["iterations"]:
+        assert np.array_equal(g["corr_index"], o["corr_index"])
+        assert np.array_equal(g["corr_dist2"], o["corr_dist2"])
+    assert np.abs(g["registered_xyz"] - o["registered_xyz"]).max() <= 1e-5 * extent
+
+
+def test_icp_p2p_vs_pcl_like_float32_estimator(ctx, pair):
+    """Against the oracle's float32 (PCL-faithful) Umeyama sums: north-star tolerances."""
+    src, tgt = pair
+    extent = float(np.ptp(tgt, axis=0).max())
+    o = orc.icp_align(src, tgt, 0.02, 50, umeyama_f32=True)
+    g = api.icp_align(src, tgt, 0.02, 50, ctx=ctx)
+    assert g["iterations"] == o["iterations"]
+    assert_transform_close(g["transformation"], o["transformation"], extent)
+    # float32 estimator sums carry ~1e-5 relative noise of their own (sequential float32 sums
+    # over ~3e4 terms), which shows up in the fitness at the few-1e-5 level
+    assert abs(g["fitness"] - o["fitness"]) <= 1e-4 * o["fitness"]
+
+
+def test_icp_p2plane_matches_oracle(ctx, pair_normals):
+    src, tgt = pair_normals
+    extent = float(np.ptp(tgt.xyz, axis=0).max())
+    for dump_it in (0, 3):
+        o = orc.icp_align(src, tgt, 0.02, 50, mode=1, dump_iteration=dump_it, want_registered=True)
+        g = api.icp_align(src, tgt, 0.02, 50, mode=1, dump_iteration=dump_it, want_registered=True, ctx=ctx)
+        assert g["iterations"] == o["iterations"] and g["state"] == o["state"]
+        assert_transform_close(g["transformation"], o["transformation"], extent)
+        assert abs(g["fitness"] - o["fitness"]) <= FIT_TOL * o["fitness"]
+        if dump_it < o["iterations"]:
+            assert np.array_equal(g["corr_index"], o["corr_index"])
+        assert np.abs(g["registered_normal"] - o["registered_normal"]).max() <= 1e-5
+
+
+def test_icp_recovers_known_motion(ctx):
+    tgt = synth.kinect_view(0, scale=0.4, backdrop="panel", noise=False)
+    T = synth.rigid(1.0, -2.0, 0.5, [0.004, -0.003, 0.002])
+    src = synth.apply_transform(np.linalg.inv(T), tgt)
+    g = api.icp_align(src, tgt, 0.05, 100, transformation_epsilon=1e-12, euclidean_fitness_epsilon=1e-9,
+                      ctx=ctx)
+    assert rot_angle(g["transformation"], T.astype(np.float32)) < 2e-4
+    assert np.abs(g["transformation"][:3, 3] - T[:3, 3]).max() < 2e-4
+    assert g["fitness"] < 1e-9
+
+
+def test_icp_criteria_and_edge_cases(ctx, pair):
+    src, tgt = pair
+    # iteration cap
+    o = orc.icp_align(src, tgt, 0.02, 3)
+    g = api.icp_align(src, tgt, 0.02, 3, ctx=ctx)
+    assert g["iterations"] == o["iterations"] == 3 and g["state"] == o["state"] == 1 and g["converged"]
+    # not enough correspondences: far apart, tiny gate -> converged False (PCL semantics)
+    far = src + np.float32(10.0)
+    o = orc.icp_align(far, tgt, 0.001, 10)
+    g = api.icp_align(far, tgt, 0.001, 10, ctx=ctx)
+    assert g["state"] == o["state"] == 5 and not g["converged"] and g["iterations"] == o["iterations"] == 0
+    assert np.array_equal(g["transformation"], np.eye(4, dtype=np.float32))
+    # PCL-default gate (sqrt(DBL_MAX)): unbounded correspondences
+    o = orc.icp_align(src[::7], tgt[::5], float(np.sqrt(np.finfo(np.float64).max)), 5)
+    g = api.icp_align(src[::7], tgt[::5], float(np.sqrt(np.finfo(np.float64).max)), 5, ctx=ctx)
+    assert g["iterations"] == o["iterations"]
+    assert np.abs(g["transformation"] - o["transformation"]).max() < 1e-5
+    # invalid arguments surface as errors, not crashes
+    with pytest.raises(api.Lc3dError):
+        api.icp_align(src, tgt, 0.02, 0, ctx=ctx)
+    with pytest.raises(api.Lc3dError):
+        api.icp_align(src, tgt, 0.02, 5, mode=1, ctx=ctx)  # p2plane without target normals
+
+
+def test_icp_pcl_aos_layout_and_resident(ctx, pair_normals):
+    """The 48-byte pcl::PointXYZRGBNormal layout and the resident (HBM) entry point give the
+    same bits as packed host arrays."""
+    src, tgt = pair_normals
+
+    def aos(hc):
+        a = np.zeros((hc.n, 12), dtype=np.float32)
+        a[:, 0:3] = hc.xyz
+        a[:, 3] = 1.0
+        a[:, 4:7] = hc.normal
+        a[:, 9] = hc.curvature
+        return HostCloud.from_pcl_aos(a)
+
+    ref = api.icp_align(src, tgt, 0.02, 30, mode=1, ctx=ctx)
+    g = api.icp_align(aos(src), aos(tgt), 0.02, 30, mode=1, ctx=ctx)
+    assert np.array_equal(g["transformation"], ref["transformation"]) and g["fitness"] == ref["fitness"]
+    ds, dt = ctx.upload(src), ctx.upload(tgt)
+    r = api.icp_align(ds, dt, 0.02, 30, mode=1, ctx=ctx)
+    assert np.array_equal(r["transformation"], ref["transformation"]) and r["fitness"] == ref["fitness"]
+    ds.free()
+    dt.free()
+
+
+def test_icp_equivariance_property(ctx, pair):
+    """Size-independent property: moving both clouds by a rigid motion M
+    conjugates the solution, T' = M T M^-1, up to float rounding."""
+    src, tgt = pair
+    M = synth.rigid(10, 20, -5, [0.3, -0.2, 0.1])
+    g0 = api.icp_align(src, tgt, 0.02, 50, ctx=ctx)
+    g1 = api.icp_align(synth.apply_transform(M, src), synth.apply_transform(M, tgt), 0.02, 50, ctx=ctx)
+    Texp = M @ g0["transformation"].astype(np.float64) @ np.linalg.inv(M)
+    assert rot_angle(g1["transformation"], Texp.astype(np.float32)) < 2e-3
+    assert abs(g1["fitness"] - g0["fitness"]) < 0.05 * g0["fitness"]
+
+
+# ------------------------------------------------------------------------------- kNN
+
+@pytest.mark.parametrize("k", [1, 8, 31, 51, 101])
+def test_knn_bit_exact(ctx, pair, k):
+    _, tgt = pair
+    oi, od = orc.KdTree(tgt).knn(tgt, k)
+    gi, gd = api.knn(tgt, k, ctx=ctx)
+    assert np.array_equal(gd, od)
+    assert np.array_equal(gi, oi)
+
+
+def test_knn_external_queries_and_small_clouds(ctx):
+    rng = np.random.default_rng(5)
+    c = rng.normal(0, 1, (20000, 3)).astype(np.float32)
+    q = rng.normal(0, 2, (3000, 3)).astype(np.float32)
+    oi, od = orc.KdTree(c).knn(q, 16)
+    gi, gd = api.knn(c, 16, queries=q, ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    # fewer points than k: missing neighbours are (-1, inf)
+    small = rng.normal(0, 1, (7, 3)).astype(np.float32)
+    oi, od = orc.KdTree(small).knn(small, 10)
+    gi, gd = api.knn(small, 10, ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    # many duplicates (ties broken by index) — more coincident points than the buffer holds
+    dup = np.repeat(rng.normal(0, 1, (40, 3)).astype(np.float32), 200, axis=0)
+    oi, od = orc.KdTree(dup).knn(dup[::50], 20)
+    gi, gd = api.knn(dup, 20, queries=dup[::50], ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+# ----------------------------------------------------------------------------- normals
+
+def test_normals_match_oracle(ctx, pair):
+    _, tgt = pair
+    for k, vp in ((30, (0.0, 0.0, 0.0)), (50, tuple(orc.centroid(tgt)[:3]))):
+        on, oc = orc.normals(tgt, k, vp)
+        gn, gc = api.normals(tgt, k, vp, ctx=ctx)
+        # angle from the cross product (arccos of a float32 dot is useless below ~5e-4 rad)
+        ang = np.arcsin(np.clip(np.linalg.norm(np.cross(on.astype(np.float64), gn.astype(np.float64)), axis=1), 0, 1))
+        ang = np.where(np.sum(on.astype(np.float64) * gn, axis=1) < 0, np.pi - ang, ang)
+        # identical neighbour sets and float32 op order; only atan2f/cosf/sinf differ between
+        # glibc and CUDA (<= 2 ulp) -> sub-microradian differences
+        assert np.nanmax(ang) < 2e-3
+        assert np.nanmedian(ang) < 1e-6
+        assert (ang < 1e-5).mean() > 0.995
+        assert np.nanmax(np.abs(gc - oc)) < 1e-3
+        assert np.isnan(gn).sum() == np.isnan(on).sum()
+
+
+def test_centroid_bit_exact(ctx, pair):
+    _, tgt = pair
+    assert np.array_equal(api.centroid(tgt, ctx=ctx), orc.centroid(tgt))
+
+
+# --------------------------------------------------------------------------------- SOR
+
+@pytest.mark.parametrize("k,mul", [(50, 1.0), (50, 5.0), (8, 0.5)])
+def test_sor_mask_bit_exact(ctx, pair, k, mul):
+    _, tgt = pair
+    rng = np.random.default_rng(k)
+    cloud = tgt.copy()
+    out = rng.choice(len(cloud), 300, replace=False)
+    cloud[out] += rng.normal(0, 0.03, (300, 3)).astype(np.float32)  # injected outliers
+    ok, omd, ost = orc.sor(cloud, k, mul)
+    gk, gmd, gst = api.sor(cloud, k, mul, ctx=ctx)
+    assert np.array_equal(gmd, omd)          # per-point mean distances, float32 bits
+    assert np.array_equal(gk, ok)            # kept-index list == mask, order preserved
+    assert np.allclose(gst, ost, rtol=1e-12)
+    okn, _, _ = orc.sor(cloud, k, mul, negative=True)
+    gkn, _, _ = api.sor(cloud, k, mul, negative=True, ctx=ctx)
+    assert np.array_equal(gkn, okn)
+    assert len(gk) + len(gkn) == len(cloud)
+
+
+# --------------------------------------------------------------------------- VoxelGrid
+
+@pytest.mark.parametrize("leaf", [0.002, 0.01, 0.05])
+def test_voxel_grid_bit_exact(ctx, pair_normals, leaf):
+    _, tgt = pair_normals
+    rng = np.random.default_rng(1)
+    rgba = rng.integers(0, 2**32, tgt.n, dtype=np.uint32)
+    cloud = HostCloud(tgt.xyz, normal=tgt.normal, rgba=rgba, curvature=tgt.curvature)
+    o = orc.voxel_grid(cloud, leaf)
+    g = api.voxel_grid(cloud, leaf, ctx=ctx)
+    assert np.array_equal(g["voxel_of_point"], o["voxel_of_point"])  # occupancy, assignment, order
+    assert np.array_equal(g["xyz"], o["xyz"])                        # centroids: same summation order
+    assert np.array_equal(g["rgba"], o["rgba"])
+    assert np.array_equal(g["curvature"], o["curvature"])
+    assert np.nanmax(np.abs(g["normal"] - o["normal"])) <= 1e-6
+
+
+def test_voxel_grid_overflow_guard_and_edges(ctx, pair):
+    _, tgt = pair
+    # leaf so small that dx*dy*dz > INT32_MAX: PCL returns the input unfiltered
+    o = orc.voxel_grid(tgt, 1e-5)
+    g = api.voxel_grid(tgt, 1e-5, ctx=ctx)
+    assert o["overflow"] and len(g["xyz"]) == len(tgt) and np.array_equal(g["xyz"], tgt)
+    # one voxel swallowing everything (all coordinates positive -> a single voxel)
+    shifted = tgt[:5000] + np.float32(10.0)
+    g = api.voxel_grid(shifted, 100.0, ctx=ctx)
+    o = orc.voxel_grid(shifted, 100.0)
+    assert len(g["xyz"]) == 1 and np.array_equal(g["xyz"], o["xyz"])
+    g = api.voxel_grid(tgt[:5000], 100.0, ctx=ctx)
+    o = orc.voxel_grid(tgt[:5000], 100.0)
+    assert np.array_equal(g["xyz"], o["xyz"]) and np.array_equal(g["voxel_of_point"], o["voxel_of_point"])
+    # idempotence-style property: filtering the centroids with the same leaf keeps their count
+    g1 = api.voxel_grid(tgt, 0.01, ctx=ctx)
+    g2 = api.voxel_grid(g1["xyz"], 0.01, ctx=ctx)
+    assert len(g2["xyz"]) <= len(g1["xyz"])
+
+
+# --------------------------------------------------------------------------- transform
+
+def test_transform_bit_exact(ctx, pair_normals):
+    src, _ = pair_normals
+    T = synth.rigid(3, -4, 5, [0.1, 0.2, -0.3]).astype(np.float32)
+    ox, on = orc.transform(src, T)
+    gx, gn = api.transform(src, T, ctx=ctx)
+    assert np.array_equal(gx, ox) and np.array_equal(gn, on)
