@@ -56,6 +56,9 @@ void lc3d_destroy(lc3d_ctx* ctx);
 /* ctx may be NULL: returns the last error of a failed lc3d_create on this thread. */
 const char* lc3d_last_error(const lc3d_ctx* ctx);
 const char* lc3d_version(void);
+/* Diagnostics of the most recently built spatial index: out[0]=cell edge, out[1..3]=grid
+ * dims, out[4]=cells, out[5]=indexed points, out[6]=bricks/occupied super-cells (or 0). */
+void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]);
 /* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
 int64_t lc3d_launch_count(const lc3d_ctx* ctx);
 

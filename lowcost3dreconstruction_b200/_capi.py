@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblc3d.so")
+LIB_PATH = os.environ.get("LC3D_LIB") or os.path.join(_HERE, "csrc", "liblc3d.so")
 
 
 class Cloud(C.Structure):
@@ -77,6 +77,7 @@ STATE_NAMES = {0: "NOT_CONVERGED", 1: "ITERATIONS", 2: "TRANSFORM", 3: "ABS_MSE"
 # Every symbol include/lc3d.h declares (tests check the library exports all of them).
 SYMBOLS = [
     "lc3d_create", "lc3d_destroy", "lc3d_last_error", "lc3d_version", "lc3d_launch_count",
+    "lc3d_debug_grid_info",
     "lc3d_cloud_upload", "lc3d_cloud_free", "lc3d_dcloud_size",
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
@@ -144,6 +145,8 @@ def _declare(lib):
     lib.lc3d_version.restype = C.c_char_p
     lib.lc3d_launch_count.argtypes = [vp]
     lib.lc3d_launch_count.restype = i64
+    lib.lc3d_debug_grid_info.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.lc3d_debug_grid_info.restype = None
     lib.lc3d_cloud_upload.argtypes = [vp, cp, C.POINTER(vp)]
     lib.lc3d_cloud_upload.restype = C.c_int
     lib.lc3d_cloud_free.argtypes = [vp, vp]

@@ -58,6 +58,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.lc3d_launch_count(self._h))
 
+    def grid_info(self) -> dict:
+        out = (C.c_double * 8)()
+        self._lib.lc3d_debug_grid_info(self._h, out)
+        return dict(cell=out[0], dims=(int(out[1]), int(out[2]), int(out[3])), cells=int(out[4]), points=int(out[5]))
+
     # ---- resident clouds -------------------------------------------------------------
     def upload(self, cloud) -> "DeviceCloud":
         hc = _hc(cloud)

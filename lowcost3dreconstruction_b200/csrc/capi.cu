@@ -20,7 +20,7 @@ thread_local std::string g_create_error;
 // scratch slots beyond the grid builder's
 enum {
   kScrRawA = kScrGridEnd, kScrRawB, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
-  kScrOutB, kScrDumpIdx, kScrDumpD2, kScrQuery, kScrMisc, kScrMisc2, kScrMisc3, kScrEnd
+  kScrOutB, kScrDumpIdx, kScrDumpD2, kScrBound, kScrPrevMatch, kScrMisc, kScrMisc2, kScrMisc3, kScrEnd
 };
 static_assert(kScrEnd <= 32, "scratch slots");
 
@@ -126,17 +126,39 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->scratch[kScrSrcWork].ensure((size_t)n * 16 + 16);
   float4* X0 = ctx->scratch[kScrSrcSorted].as<float4>();
   float4* X = ctx->scratch[kScrSrcWork].as<float4>();
+  ctx->scratch[kScrBound].ensure((size_t)n * 4 + 16);
+  float* Bnd = ctx->scratch[kScrBound].as<float>();
+  ctx->scratch[kScrPrevMatch].ensure((size_t)n * 4 + 16);
+  int* Mj = ctx->scratch[kScrPrevMatch].as<int>();
   sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0);
   if (n > 0) LC3D_CUDA(cudaMemcpyAsync(X, X0, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
   ctx->tm[1].stop(st);
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));
   IcpState* d_state = ctx->scratch[kScrState].as<IcpState>();
-  const int nblk = std::max(1, div_up(n, kIcpThreads));
-  ctx->scratch[kScrPartials].ensure((size_t)kNvP2Plane * nblk * 8);
+  const int nblk_fit = std::max(1, div_up(n, kIcpThreads));
+  const int nblk = nblk_fit;
+  ctx->scratch[kScrPartials].ensure((size_t)kNvP2Plane * std::max(nblk, nblk_fit) * 8);
   double* partials = ctx->scratch[kScrPartials].as<double>();
   IcpConfig cfg;
   cfg.gate = gate_from_distance(p->max_correspondence_distance);
+  if (std::isinf(cfg.gate)) {
+    cfg.gate_ext = INFINITY;
+    cfg.gate_dist = INFINITY;
+    cfg.margin_slack = 0.0f;
+    cfg.slack_floor = INFINITY;  // no skipping without a finite gate
+  } else {
+    // searches use an extended gate so that rejected queries learn how far beyond the gate
+    // their nearest neighbour is (the slack that lets later iterations skip them)
+    const double r = std::sqrt((double)cfg.gate);
+    const double margin = std::max(0.25 * r, 2.0 * (double)G.v.c);
+    cfg.gate_dist = std::nextafterf((float)r, INFINITY);
+    float ge = (float)((r + margin) * (r + margin));
+    cfg.gate_ext = std::isfinite(ge) ? ge : INFINITY;
+    cfg.slack_floor = (float)(1e-4 * (r + margin));
+    cfg.margin_slack = std::isfinite(ge) ? (float)(margin * 0.9999) : 0.0f;
+    if (!std::isfinite(ge)) cfg.slack_floor = INFINITY;
+  }
   cfg.max_iterations = p->max_iterations;
   cfg.rot_thr = 1.0 - p->transformation_epsilon;
   cfg.transl_thr = p->transformation_epsilon;
@@ -144,6 +166,13 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   cfg.abs_mse = 1e-12;
   cfg.dump_iteration = p->dump_iteration;
   cfg.mode = p->mode;
+  cfg.stats = nullptr;
+  const bool want_stats = std::getenv("LC3D_STATS") != nullptr;
+  if (want_stats) {
+    ctx->scratch[kScrMisc2].ensure(sizeof(SearchStats) * (p->max_iterations + 1));
+    cfg.stats = ctx->scratch[kScrMisc2].as<SearchStats>();
+    LC3D_CUDA(cudaMemsetAsync(cfg.stats, 0, sizeof(SearchStats) * (p->max_iterations + 1), st));
+  }
   int32_t* d_dump_idx = nullptr;
   float* d_dump_d2 = nullptr;
   const bool dump = out && (out->corr_index || out->corr_dist2) && p->dump_iteration >= 0 && n > 0;
@@ -157,19 +186,27 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   }
   ctx->tm[2].start(st);
   LC3D_LAUNCH(ctx, icp_state_init, 1, 32, 0, d_state);
+  std::vector<cudaEvent_t> iter_ev;
+  if (want_stats) {
+    iter_ev.resize(p->max_iterations + 1);
+    for (auto& e : iter_ev) LC3D_CUDA(cudaEventCreate(&e));
+    LC3D_CUDA(cudaEventRecord(iter_ev[0], st));
+  }
   for (int it = 0; it < p->max_iterations; ++it) {
+    if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
     if (p->mode == LC3D_ICP_POINT_TO_PLANE)
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state,
-                  cfg, G.v, X, n, partials, d_dump_idx, d_dump_d2);
+                  cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
     else
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT>, nblk, kIcpThreads, 0, d_state,
-                  cfg, G.v, X, n, partials, d_dump_idx, d_dump_d2);
+                  cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
   }
+  if (want_stats) LC3D_CUDA(cudaEventRecord(iter_ev[p->max_iterations], st));
   ctx->tm[2].stop(st);
   // ---- getFitnessScore ----
   ctx->tm[3].start(st);
   if (p->compute_fitness)
-    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk, kIcpThreads, 0, d_state, G.v, X0, n, partials);
+    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kIcpThreads, 0, d_state, G.v, X0, Mj, n, partials);
   ctx->tm[3].stop(st);
   // ---- results ----
   ctx->tm[4].start(st);
@@ -198,6 +235,23 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->tm[4].stop(st);
   ctx->tm[5].stop(st);
   LC3D_CUDA(cudaStreamSynchronize(st));
+  if (want_stats) {
+    std::vector<SearchStats> hs(p->max_iterations);
+    LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * p->max_iterations, cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "[lc3d stats] cell %.5f dims %dx%dx%d n_src %d\n", G.v.c, G.v.dx, G.v.dy, G.v.dz, n);
+    for (int it = 0; it < h_state->iter + 1 && it < p->max_iterations; ++it) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, iter_ev[it], iter_ev[it + 1]);
+      std::fprintf(stderr, "[lc3d stats] it %2d kernel %.1f us\n", it, ms * 1e3f);
+    }
+    for (auto& e : iter_ev) cudaEventDestroy(e);
+    for (int it = 0; it < h_state->iter; ++it)
+      std::fprintf(stderr,
+                   "[lc3d stats] it %2d searched %7llu prev-seed %7llu probe %7llu borrowed %6llu walked %7llu "
+                   "fallback %6llu | warp cand-iters %9llu rows %8llu | warp cycles avg %llu max %llu, max batch %llu\n",
+                   it, hs[it].c[0], hs[it].c[1], hs[it].c[2], hs[it].c[3], hs[it].c[4], hs[it].c[5],
+                   hs[it].c[6], hs[it].c[7], hs[it].c[8], hs[it].c[9], hs[it].c[10]);
+  }
   std::memcpy(res->transformation, h_state->Tfinal, sizeof res->transformation);
   res->converged = h_state->converged;
   res->iterations = h_state->iter;
@@ -302,6 +356,18 @@ const char* lc3d_last_error(const lc3d_ctx* ctx) {
 }
 
 int64_t lc3d_launch_count(const lc3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]) {
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (!ctx || !ctx->grid) return;
+  const GridDev& g = ctx->grid->v;
+  out[0] = g.c;
+  out[1] = g.dx;
+  out[2] = g.dy;
+  out[3] = g.dz;
+  out[4] = (double)ctx->grid->ncell;
+  out[5] = g.n;
+}
 
 int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out) {
   if (!out || !host) return LC3D_ERR_INVALID;

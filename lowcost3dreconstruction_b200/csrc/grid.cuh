@@ -322,20 +322,31 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   g.nrm = nrm ? G.nrm.as<float4>() : nullptr;
 }
 
-// Orders `xyz` (n float4) by the cell it falls into in grid g (clamped), for query
-// locality: queries consecutive in memory walk the same cell rows.  out[j].w = bits(orig idx).
+// Orders `xyz` (n float4) along a Morton (Z-order) curve over the cells of grid g (clamped),
+// for query locality: G consecutive queries form a compact 3-D patch, so the lanes of a
+// tile group share one small search region.  (The TARGET stays in linear x-fastest cell
+// order: that is what makes x-runs of cells contiguous.)  out[j].w = bits(orig idx).
+__device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
 __global__ void __launch_bounds__(256)
-    query_keys(const float4* __restrict__ p, int n, GridDev g, uint32_t* __restrict__ keys,
+    query_keys(const float4* __restrict__ p, int n, GridDev g, int shift, uint32_t* __restrict__ keys,
                uint32_t* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = p[i];
-  uint32_t key = (uint32_t)g.dx * g.dy * g.dz;
+  uint32_t key = 0x40000000u;  // non-finite queries sort last
   if (finite3(q.x, q.y, q.z)) {
     int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
     int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
-    key = (uint32_t)((iz * g.dy + iy) * g.dx + ix);
+    key = morton_spread10((uint32_t)ix >> shift) | (morton_spread10((uint32_t)iy >> shift) << 1) |
+          (morton_spread10((uint32_t)iz >> shift) << 2);
   }
   keys[i] = key;
   vals[i] = (uint32_t)i;
@@ -353,10 +364,13 @@ inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz
   ctx->scratch[kScrScan].ensure(scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile)) + 64);
   uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
   uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
-  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, keys, vals);
+  int maxdim = std::max(G.v.dx, std::max(G.v.dy, G.v.dz));
+  int shift = 0;
+  while ((maxdim >> shift) > 1024) ++shift;  // 10 bits per axis
+  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, keys, vals);
   SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
                  ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
-  radix_sort_pairs(ctx, keys, vals, n, bit_length((uint32_t)G.ncell), ss);
+  radix_sort_pairs(ctx, keys, vals, n, 31, ss);
   LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, (const float4*)nullptr, vals, n,
               out_sorted, (float4*)nullptr);
 }

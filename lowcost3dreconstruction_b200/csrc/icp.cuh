@@ -41,6 +41,10 @@ struct IcpState {
 
 struct IcpConfig {
   float gate;         // largest float <= max_correspondence_distance^2
+  float gate_ext;     // (gate_dist + margin)^2: searches run against this extended gate
+  float gate_dist;    // sqrt(gate), rounded up
+  float margin_slack; // slack learnt when nothing lies within the extended gate
+  float slack_floor;  // slacks at or below this are treated as unknown (float safety)
   int max_iterations;
   double rot_thr;     // 1 - transformation_epsilon
   double transl_thr;  // transformation_epsilon (squared translation)
@@ -48,6 +52,7 @@ struct IcpConfig {
   double abs_mse;     // 1e-12
   int dump_iteration;
   int mode;
+  SearchStats* stats;  // per-iteration search statistics (LC3D_STATS=1) or null
 };
 
 __global__ void icp_state_init(IcpState* st) {
@@ -292,15 +297,86 @@ __device__ __forceinline__ void last_block_reduce(const double* __restrict__ par
   }
 }
 
-// One ICP iteration.  X: working copy of the source (float4, cell-sorted order, w =
-// original index), transformed in place.  One thread per source point.
+// Butterfly reduce-scatter of 32 per-lane values: after 5 exchange rounds lane L holds the
+// warp total of value L.  31 shuffles instead of 32 x 5, fixed summation tree (deterministic).
+// The values are produced by `val(i)` (i compile-time after unrolling) inside the first
+// round, so only 16 doubles are ever live.
+template <typename F>
+__device__ __forceinline__ double warp_reduce_scatter32(F val, int lane) {
+  const unsigned full = 0xffffffffu;
+  double v[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double lo = val(i), hi = val(i + 16);
+      const double send = up ? lo : hi;
+      const double keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+  }
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, h);
+    }
+  }
+  return v[0];
+}
+
+// estimator value i of one correspondence (compile-time i): point-to-plane layout
+// [0..20] J^T J upper triangle, [21..26] J^T r, [27] d2, [28] 1; point-to-point layout
+// [0..2] s, [3..5] d, [6..14] d s^T, [15] d2, [16] 1.
+__device__ __forceinline__ double p2plane_value(int i, const double* J, double r, double d2, double one) {
+  if (i < 21) {
+    // (row, col) of the i-th upper-triangle entry; folds to constants once i is unrolled
+    const int a = i < 6 ? 0 : i < 11 ? 1 : i < 15 ? 2 : i < 18 ? 3 : i < 20 ? 4 : 5;
+    const int base = a == 0 ? 0 : a == 1 ? 6 : a == 2 ? 11 : a == 3 ? 15 : a == 4 ? 18 : 20;
+    return J[a] * J[a + (i - base)];
+  }
+  if (i < 27) return J[i - 21] * r;
+  if (i == 27) return d2;
+  if (i == 28) return one;
+  return 0.0;
+}
+__device__ __forceinline__ double p2p_value(int i, const double* sv, const double* dv, double d2, double one) {
+  if (i < 3) return sv[i];
+  if (i < 6) return dv[i - 3];
+  if (i < 15) return dv[(i - 6) / 3] * sv[(i - 6) % 3];
+  if (i == 15) return d2;
+  if (i == 16) return one;
+  return 0.0;
+}
+
+// One ICP iteration.  X: working copy of the source (float4, Morton order, w = original
+// index), transformed in place.  One thread per source point; the 32 estimator sums of a warp
+// are reduced with one butterfly reduce-scatter (lane L ends up with value L), combined per
+// block in a fixed order, written as one partial row per block, and the last block to finish
+// reduces the rows and solves.
+//
+// Per-query memory across iterations (temporal coherence):
+//   Mj[i]  : sorted-target position of the previous match (seed: its distance is an exact
+//            upper bound on the nearest-neighbour distance, which sizes the ball walk);
+//   Bnd[i] : < 0  -> no target point within gate_distance + (-Bnd): while the accumulated
+//            motion stays below that slack the query provably has no correspondence and
+//            the search is skipped;  +inf -> nothing known.
+// Searches run against an extended gate (r + margin)^2 so that rejected queries learn a
+// slack; a correspondence is emitted iff d2 <= gate exactly as PCL does.
+#ifndef LC3D_ICP_MINBLOCKS
+#define LC3D_ICP_MINBLOCKS 3
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kIcpThreads)
+__global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
     icp_iteration_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const GridDev g,
-                         float4* __restrict__ X, int n, double* __restrict__ partials,
-                         int32_t* __restrict__ dump_idx, float* __restrict__ dump_d2) {
+                         float4* __restrict__ X, float* __restrict__ Bnd, int* __restrict__ Mj, int n,
+                         double* __restrict__ partials, int32_t* __restrict__ dump_idx,
+                         float* __restrict__ dump_d2) {
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
-  __shared__ double warp_part[kIcpThreads / 32][NV];
+  __shared__ double warp_part[kIcpThreads / 32][32];
   __shared__ double red[NV];
   __shared__ float sT[16];
   __shared__ int s_flags[2];
@@ -313,94 +389,89 @@ __global__ void __launch_bounds__(kIcpThreads)
   if (s_flags[0]) return;
   const int iter = s_flags[1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = i < n;
-  float4 q = active ? X[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-  active = active && finite3(q.x, q.y, q.z);
-  if (active && iter > 0) {  // transformCloud with the previous iteration's T
-    float x = xform_row(sT, 0, q.x, q.y, q.z);
-    float y = xform_row(sT, 1, q.x, q.y, q.z);
-    float z = xform_row(sT, 2, q.x, q.y, q.z);
-    q.x = x;
-    q.y = y;
-    q.z = z;
-    X[i] = q;
-  }
-  Best b = nn_search(g, active, q.x, q.y, q.z, cfg.gate);
-  const bool has = active && b.j >= 0;
-  if (dump_idx && iter == cfg.dump_iteration && i < n) {
-    const int oi = __float_as_int(q.w);
-    dump_idx[oi] = has ? b.oi : -1;
-    dump_d2[oi] = has ? b.d2 : INFINITY;
-  }
-  // ---- estimator sums, fp64 ------------------------------------------------------
-  const unsigned any = __ballot_sync(0xffffffffu, has);
-  if (any) {
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has) d = __ldg(&g.pts[b.j]);
-    if (MODE == LC3D_ICP_POINT_TO_PLANE) {
-      double J[6] = {0, 0, 0, 0, 0, 0}, r = 0;
-      if (has) {
-        const float4 nn = __ldg(&g.nrm[b.j]);
-        if (finite3(nn.x, nn.y, nn.z)) {
-          // float32 products widened to double, as TransformationEstimationPointToPlaneLLS
-          J[0] = (double)__fsub_rn(__fmul_rn(nn.z, q.y), __fmul_rn(nn.y, q.z));
-          J[1] = (double)__fsub_rn(__fmul_rn(nn.x, q.z), __fmul_rn(nn.z, q.x));
-          J[2] = (double)__fsub_rn(__fmul_rn(nn.y, q.x), __fmul_rn(nn.x, q.y));
-          J[3] = nn.x;
-          J[4] = nn.y;
-          J[5] = nn.z;
-          float rr = __fmul_rn(nn.x, d.x);
-          rr = __fadd_rn(rr, __fmul_rn(nn.y, d.y));
-          rr = __fadd_rn(rr, __fmul_rn(nn.z, d.z));
-          rr = __fsub_rn(rr, __fmul_rn(nn.x, q.x));
-          rr = __fsub_rn(rr, __fmul_rn(nn.y, q.y));
-          rr = __fsub_rn(rr, __fmul_rn(nn.z, q.z));
-          r = (double)rr;
-        }
-      }
-      int k = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int c = a; c < 6; ++c) {
-          double s = warp_sum(J[a] * J[c]);
-          if (lane == 0) warp_part[w][k] = s;
-          ++k;
-        }
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        double s = warp_sum(J[a] * r);
-        if (lane == 0) warp_part[w][21 + a] = s;
-      }
-    } else {
-      const double sx = has ? (double)q.x : 0.0, sy = has ? (double)q.y : 0.0, sz = has ? (double)q.z : 0.0;
-      const double dx = d.x, dy = d.y, dz = d.z;
-      const double sv[3] = {sx, sy, sz}, dv[3] = {dx, dy, dz};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        double s = warp_sum(sv[a]);
-        if (lane == 0) warp_part[w][a] = s;
-        s = warp_sum(dv[a]);
-        if (lane == 0) warp_part[w][3 + a] = s;
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          double s = warp_sum(dv[a] * sv[c]);
-          if (lane == 0) warp_part[w][6 + a * 3 + c] = s;
-        }
+  SearchStats* stats = cfg.stats ? cfg.stats + iter : nullptr;
+  double acc = 0.0;  // lane L: total of estimator value L
+  {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < n;
+    float4 q = active ? X[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float bnd = (active && iter > 0) ? Bnd[i] : INFINITY;
+    const int seed_j = (active && iter > 0) ? Mj[i] : -1;
+    active = active && finite3(q.x, q.y, q.z);
+    float delta = 0.0f;
+    if (active && iter > 0) {  // transformCloud with the previous iteration's T
+      const float x = xform_row(sT, 0, q.x, q.y, q.z);
+      const float y = xform_row(sT, 1, q.x, q.y, q.z);
+      const float z = xform_row(sT, 2, q.x, q.y, q.z);
+      const float mx = x - q.x, my = y - q.y, mz = z - q.z;
+      delta = sqrtf(mx * mx + my * my + mz * mz) * 1.00001f;
+      q.x = x;
+      q.y = y;
+      q.z = z;
+      X[i] = q;
     }
-    double s = warp_sum(has ? (double)b.d2 : 0.0);
-    if (lane == 0) {
-      warp_part[w][NV - 2] = s;
-      warp_part[w][NV - 1] = (double)__popc(any);
+    bool skip = false;
+    if (active && bnd < 0.0f) {
+      const float slack = -bnd - delta;
+      if (slack > cfg.slack_floor) {
+        skip = true;
+        bnd = -slack;
+      }
     }
-  } else if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) warp_part[w][k] = 0.0;
+    const Best b = nn_search_seeded(g, active && !skip, q.x, q.y, q.z, cfg.gate_ext, seed_j, stats);
+    const bool found = active && !skip && b.j >= 0;
+    const bool has = found && b.d2 <= cfg.gate;
+    if (active && !skip) {
+      if (found) {
+        if (has) {
+          bnd = INFINITY;
+        } else {  // exact nearest neighbour lies beyond the gate: nothing within d
+          const float slack = sqrtf(b.d2) * 0.99999f - cfg.gate_dist;
+          bnd = slack > cfg.slack_floor ? -slack : INFINITY;
+        }
+      } else {
+        bnd = cfg.margin_slack > cfg.slack_floor ? -cfg.margin_slack : INFINITY;
+      }
+    }
+    if (i < n) {
+      Bnd[i] = bnd;
+      Mj[i] = skip ? seed_j : (found ? b.j : -1);
+    }
+    if (dump_idx && iter == cfg.dump_iteration && i < n) {
+      const int oi = __float_as_int(q.w);
+      dump_idx[oi] = has ? b.oi : -1;
+      dump_d2[oi] = has ? b.d2 : INFINITY;
+    }
+    // ---- estimator sums, fp64 ----------------------------------------------------
+    if (__any_sync(0xffffffffu, has)) {
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has) d = __ldg(&g.pts[b.j]);
+      const double d2v = has ? (double)b.d2 : 0.0, one = has ? 1.0 : 0.0;
+      if (MODE == LC3D_ICP_POINT_TO_PLANE) {
+        double J[6] = {0, 0, 0, 0, 0, 0}, r = 0;
+        if (has) {
+          const float4 nn = __ldg(&g.nrm[b.j]);
+          if (finite3(nn.x, nn.y, nn.z)) {
+            // float32 products widened to double, as TransformationEstimationPointToPlaneLLS
+            J[0] = (double)(nn.z * q.y - nn.y * q.z);
+            J[1] = (double)(nn.x * q.z - nn.z * q.x);
+            J[2] = (double)(nn.y * q.x - nn.x * q.y);
+            J[3] = nn.x;
+            J[4] = nn.y;
+            J[5] = nn.z;
+            r = (double)(nn.x * d.x + nn.y * d.y + nn.z * d.z - nn.x * q.x - nn.y * q.y - nn.z * q.z);
+          }
+        }
+        acc += warp_reduce_scatter32([&](int i) { return p2plane_value(i, J, r, d2v, one); }, lane);
+      } else {
+        const double sv[3] = {has ? (double)q.x : 0.0, has ? (double)q.y : 0.0, has ? (double)q.z : 0.0};
+        const double dv[3] = {d.x, d.y, d.z};
+        acc += warp_reduce_scatter32([&](int i) { return p2p_value(i, sv, dv, d2v, one); }, lane);
+      }
+    }
   }
+  // ---- block combine (fixed order) -> one partial row per block -----------------------
+  warp_part[w][lane] = acc;
   __syncthreads();
   const int nblk = gridDim.x;
   if (threadIdx.x < NV) {
@@ -430,7 +501,7 @@ __global__ void __launch_bounds__(kIcpThreads)
 // point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
 __global__ void __launch_bounds__(kIcpThreads)
     icp_fitness_kernel(IcpState* __restrict__ st, const GridDev g, const float4* __restrict__ src0,
-                       int n, double* __restrict__ partials) {
+                       const int* __restrict__ Mj, int n, double* __restrict__ partials) {
   __shared__ double wsum[kIcpThreads / 32], wcnt[kIcpThreads / 32];
   __shared__ float sT[16];
   __shared__ double red[2];
@@ -444,7 +515,10 @@ __global__ void __launch_bounds__(kIcpThreads)
   const float x = xform_row(sT, 0, q.x, q.y, q.z);
   const float y = xform_row(sT, 1, q.x, q.y, q.z);
   const float z = xform_row(sT, 2, q.x, q.y, q.z);
-  Best b = nn_search(g, active, x, y, z, INFINITY);
+  // seeded by the last iteration's matches (the final pose differs from the incremental one
+  // only by float rounding), unbounded: every source point counts
+  const int seed_j = (active && Mj) ? Mj[i] : -1;
+  Best b = nn_search_seeded(g, active, x, y, z, INFINITY, seed_j, nullptr);
   const bool has = active && b.j >= 0;
   double s = warp_sum(has ? (double)b.d2 : 0.0);
   unsigned any = __ballot_sync(0xffffffffu, has);

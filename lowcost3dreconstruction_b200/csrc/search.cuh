@@ -210,6 +210,171 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
   b = lb;
 }
 
+// Optional search statistics (LC3D_STATS=1): [0] queries searched, [1] seeded by the previous
+// match, [2] seeded/proven by the 3x3x3 probe, [3] seeded by a warp neighbour, [4] ball-walked,
+// [5] warp-cooperative fallbacks, [6] candidate loop iterations (warp-level), [7] rows (warp).
+struct SearchStats {
+  unsigned long long c[12];  // [8] sum of per-warp cycles, [9] max per-warp cycles, [10] max batch cycles
+};
+__device__ __forceinline__ void stat_add(SearchStats* st, int k, unsigned long long v) {
+  if (st && v) atomicAdd(&st->c[k], v);
+}
+
+// ---- ball walk -------------------------------------------------------------------------
+// Given a valid candidate (b.d2 = squared distance to some target point, or the gate), the
+// exact nearest neighbour lies in the ball of that radius around the query.  Each lane walks
+// the cell rows that intersect ITS ball — rows culled by their y/z slab distance against the
+// shrinking bound, the x-run of each row clipped to the ball — so the result is exact by
+// construction.  The row loops run over the warp-wide window (lockstep), lanes mask
+// themselves out of rows outside their own ball.
+constexpr int kBallMaxW = 12;  // window half-width (cells) beyond which phase 2 takes over
+
+__device__ __forceinline__ int ball_halfwidth(const GridDev& g, float d2) {
+  const float w = sqrtf(d2) * g.inv_c * 1.0001f + 2.0f * kCellSlack;
+  return w < 1.0e6f ? (int)ceilf(w) : 0x3fffffff;
+}
+
+// Walks the cell rows that intersect the lane's ball: rows culled by their y/z slab distance
+// against the shrinking bound, the x-run of each row clipped to the ball.  The row loops run
+// over the warp-wide window (lockstep); lanes mask themselves out of rows outside their ball.
+__device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const QueryCell& qc, float qx,
+                                          float qy, float qz, Best& b, unsigned* n_cand,
+                                          unsigned* n_rows) {
+  const unsigned full = 0xffffffffu;
+  const float inv_c2 = 1.0f / (g.c * g.c * 0.9999f);
+  int W = act ? ball_halfwidth(g, b.d2) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) W = max(W, __shfl_xor_sync(full, W, o));
+  for (int dz = -W; dz <= W; ++dz) {
+    const int zz = qc.iz + dz;
+    const float gz = slab_gap(qc.fz, zz, zz);
+    const float gz2 = gz * gz;
+    const bool zok = act && (unsigned)zz < (unsigned)g.dz;
+    for (int dy = -W; dy <= W; ++dy) {
+      const int yy = qc.iy + dy;
+      uint32_t s = 0, e = 0;
+      if (zok && (unsigned)yy < (unsigned)g.dy) {
+        const float gy = slab_gap(qc.fy, yy, yy);
+        const float rem = b.d2 * inv_c2 - (gy * gy + gz2);
+        if (rem >= 0.0f) {
+          const float wx = sqrtf(rem) + 2.0f * kCellSlack;
+          const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
+          if (xa <= xb) {
+            const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+            s = __ldg(row + xa);
+            e = __ldg(row + xb + 1);
+          }
+        }
+      }
+      if (n_rows) {
+        *n_rows += 1;
+        *n_cand += e - s;
+      }
+      for (uint32_t j = s; j < e; ++j) {
+        const float4 p = __ldg(&g.pts[j]);
+        const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+        const int oi = __float_as_int(p.w);
+        const bool better = d2 < b.d2 || (d2 == b.d2 && oi < b.oi);
+        b.d2 = better ? d2 : b.d2;
+        b.j = better ? (int)j : b.j;
+        b.oi = better ? oi : b.oi;
+      }
+    }
+  }
+}
+
+// Exact gated 1-NN for one query per thread, seeded.  All 32 lanes must call.
+// seed_j: position (sorted target order) of a plausible neighbour, e.g. the previous
+// iteration's match, or -1.  gate may be +inf (unbounded): lanes whose ball is too large for
+// the walk (or that found no candidate at all) go through the warp-cooperative ring search.
+__device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, float qx, float qy,
+                                                 float qz, float gate, int seed_j, SearchStats* stats) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  Best b;
+  b.d2 = gate;
+  b.j = -1;
+  b.oi = 0x7fffffff;
+  bool need = active && g.n > 0;
+  const QueryCell qc = query_cell(g, qx, qy, qz);
+  // 1. seed from the previous match
+  bool seeded = false;
+  if (need && seed_j >= 0) {
+    consider(__ldg(&g.pts[seed_j]), seed_j, qx, qy, qz, b);
+    seeded = b.j >= 0;
+  }
+  const unsigned n_prev = stats ? __popc(__ballot_sync(full, seeded)) : 0;
+  // 2. unseeded lanes probe their 3x3x3 block (this may already prove the result)
+  bool probed = false;
+  if (need && !seeded) {
+    if (nn_phase1(g, qc, qx, qy, qz, b)) need = false;
+    probed = b.j >= 0;
+  }
+  // 3. lanes that still have no candidate borrow a warp neighbour's match as a seed
+  {
+    const unsigned have = __ballot_sync(full, b.j >= 0);
+    const bool want = need && b.j < 0;
+    if (have && __any_sync(full, want)) {
+      // nearest lane (in lane index = Morton order) that has a candidate
+      const unsigned lower = have & ((1u << lane) - 1u), upper = have & ~((2u << lane) - 1u);
+      int src = lane;
+      if (lower && upper) {
+        const int lo = 31 - __clz(lower), hi = __ffs(upper) - 1;
+        src = (lane - lo <= hi - lane) ? lo : hi;
+      } else if (lower) {
+        src = 31 - __clz(lower);
+      } else if (upper) {
+        src = __ffs(upper) - 1;
+      }
+      const int sj = __shfl_sync(full, b.j, src);
+      if (want && src != lane && sj >= 0) consider(__ldg(&g.pts[sj]), sj, qx, qy, qz, b);
+    }
+  }
+  const bool borrowed = need && !seeded && !probed && b.j >= 0;
+  // 4. ball walk for every lane whose ball is small enough, warp-cooperative rings otherwise
+  const int Wl = need ? ball_halfwidth(g, b.d2) : 0;
+  const bool walk = need && Wl <= kBallMaxW;
+  unsigned n_cand = 0, n_rows = 0;
+  if (__any_sync(full, walk))
+    ball_walk(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
+  if (walk) need = false;
+  unsigned todo = __ballot_sync(full, need);
+  if (stats) {
+    unsigned mc = n_cand, mr = n_rows;
+    for (int o = 16; o > 0; o >>= 1) {
+      mc = max(mc, __shfl_xor_sync(full, mc, o));
+      mr = max(mr, __shfl_xor_sync(full, mr, o));
+    }
+    const unsigned na = __popc(__ballot_sync(full, active && g.n > 0));
+    const unsigned npb = __popc(__ballot_sync(full, probed)), nbr = __popc(__ballot_sync(full, borrowed));
+    const unsigned nw = __popc(__ballot_sync(full, walk));
+    if (lane == 0) {
+      stat_add(stats, 0, na);
+      stat_add(stats, 1, n_prev);
+      stat_add(stats, 2, npb);
+      stat_add(stats, 3, nbr);
+      stat_add(stats, 4, nw);
+      stat_add(stats, 5, __popc(todo));
+      stat_add(stats, 6, mc);
+      stat_add(stats, 7, mr);
+    }
+  }
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    Best wb;
+    wb.d2 = __shfl_sync(full, b.d2, src);
+    wb.j = __shfl_sync(full, b.j, src);
+    wb.oi = __shfl_sync(full, b.oi, src);
+    const float wx = __shfl_sync(full, qx, src);
+    const float wy = __shfl_sync(full, qy, src);
+    const float wz = __shfl_sync(full, qz, src);
+    nn_phase2_warp(g, wx, wy, wz, wb);
+    if (lane == src) b = wb;
+  }
+  return b;
+}
+
 // Full exact 1-NN for one query per thread.  MUST be called by all 32 lanes of every
 // warp (inactive lanes pass active=false).  gate: accept only d2 <= gate (+inf = none).
 __device__ __forceinline__ Best nn_search(const GridDev& g, bool active, float qx, float qy,
