@@ -1,0 +1,151 @@
+"""CLI contract of the four drop-in tools.  The argument handling and
+failure paths run without a GPU; the end-to-end runs are marked gpu."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lowcost3dreconstruction_b200 import synth
+from tests import plyutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "lowcost3dreconstruction_b200", "tools", "bin")
+TOOLS = ["fine_registration", "normal_estimation", "cloud_downsampling", "outlier_removal"]
+
+
+def run(tool, *args):
+    p = subprocess.run([os.path.join(BIN, tool), *args], capture_output=True, text=True, timeout=300)
+    return p.returncode, p.stdout, p.stderr
+
+
+@pytest.mark.parametrize("tool", TOOLS)
+def test_help_exits_zero(tool):
+    rc, out, err = run(tool, "--help")
+    assert rc == 0 and "Options:" in out and "-i [ --input ] arg" in out and "-h [ --help ]" in out
+    rc2, out2, _ = run(tool, "-h")
+    assert rc2 == 0 and out2 == out
+
+
+def test_help_lists_reference_options_and_defaults():
+    _, out, _ = run("fine_registration", "--help")
+    for o in ("--distance_threshold arg (=0.10000000000000001)", "--max_iterations arg (=50)",
+              "--transformation_epsilon arg (=1.0000000000000001e-09)", "--euclidean_fitness_epsilon arg (=0.001)",
+              "-t [ --target ] arg", "-a [ --accumulated ] arg"):
+        assert o in out
+    _, out, _ = run("normal_estimation", "--help")
+    assert out.startswith("Estimate a set of normals for all the points in the input dataset.")
+    for o in ("-n [ --neighbors ] arg (=50)", "-r [ --reverse_normals ]", "-c [ --centroid ]", "-z [ --origin ]"):
+        assert o in out
+    _, out, _ = run("cloud_downsampling", "--help")
+    assert "-s [ --leaf_size ] arg (=1)" in out
+    _, out, _ = run("outlier_removal", "--help")
+    assert "-f [ --outliers_file ]" in out and "-d [ --dev_mult ] arg (=1)" in out
+
+
+@pytest.mark.parametrize("tool", TOOLS)
+def test_missing_mandatory_options(tool):
+    rc, out, err = run(tool)
+    assert rc == 255  # return -1
+    assert err.startswith("Correct mode of use: ") and "-i input.ply" in err and "-o output.ply [opts]" in err
+    if tool == "fine_registration":
+        assert "-t target.ply" in err
+
+
+def test_option_errors():
+    rc, _, err = run("fine_registration", "--bogus", "1")
+    assert rc == 255 and err.strip() == "ERROR: unrecognised option '--bogus'"
+    rc, _, err = run("fine_registration", "-i")
+    assert rc == 255 and "the required argument for option '--input' is missing" in err
+    rc, _, err = run("fine_registration", "-i", "a", "-t", "b", "-o", "c", "--max_iterations", "0")
+    assert rc == 255 and err.strip() == "max_iterations needs to be greater than zero."
+    rc, _, err = run("normal_estimation", "-i", "a", "-o", "b", "-c", "-z")
+    assert rc == 255 and "not possible to use the centroid and origin as viewpoint at the same time" in err
+    rc, _, err = run("outlier_removal", "-i", "a", "-o", "b", "--neighbors", "-3")
+    assert rc == 255 and "is invalid" in err
+    # unambiguous long prefixes are accepted, as with boost's default style
+    rc, _, err = run("fine_registration", "--inp", "/nonexistent.ply", "--tar", "x", "--out", "y", "--dist", "0.02")
+    assert rc == 255 and err.strip() == "Couldn't load input cloud file"
+
+
+def test_load_failures(tmp_path):
+    rc, _, err = run("cloud_downsampling", "-i", "/nonexistent.ply", "-o", str(tmp_path / "o.ply"))
+    assert rc == 255 and err.strip() == "Couldn't load input point cloud: /nonexistent.ply"
+    good = str(tmp_path / "g.ply")
+    plyutil.write_capture_ascii(good, np.zeros((3, 3)))
+    rc, out, err = run("fine_registration", "-i", good, "-t", "/nonexistent.ply", "-o", str(tmp_path / "o.ply"))
+    assert rc == 255 and err.strip() == "Couldn't load input target file"
+    assert out.startswith("Loaded 3 data points from " + good)
+
+
+# ------------------------------------------------------------------------------- GPU runs
+
+@pytest.fixture(scope="module")
+def ply_pair(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ply")
+    # the capture tool's ASCII PLY keeps 6 decimals: the tools see exactly these values
+    tgt = np.round(synth.kinect_view(0, scale=0.2, backdrop="panel").astype(np.float64), 6).astype(np.float32)
+    src = np.round(synth.kinect_view(1, scale=0.2, backdrop="panel").astype(np.float64), 6).astype(np.float32)
+    plyutil.write_capture_ascii(str(d / "src.ply"), src)
+    plyutil.write_capture_ascii(str(d / "tgt.ply"), tgt)
+    return d, src, tgt
+
+
+@pytest.mark.gpu
+def test_pipeline_end_to_end(ply_pair, ctx):
+    from lowcost3dreconstruction_b200 import api
+    d, src, tgt = ply_pair
+    s, t = str(d / "src.ply"), str(d / "tgt.ply")
+    # outlier_removal in place (scripts/alignment.sh:99 uses -i F -o F), with the outliers file
+    t2 = str(d / "tgt_f.ply")
+    rc, out, err = run("outlier_removal", "-i", t, "-o", t2, "--neighbors", "20", "--dev_mult", "2.0", "-f")
+    assert rc == 0, err
+    assert out.startswith("Cloud before filtering: \nheader: seq: 0 stamp: 0 frame_id: \n\npoints[]: %d\nwidth: %d\nheight: 1\nis_dense: 1\n" % (len(tgt), len(tgt)))
+    kept, _, _ = api.sor(tgt, 20, 2.0, ctx=ctx)
+    f = plyutil.read_pcl_binary(t2)
+    assert len(f) == len(kept) and np.array_equal(f["xyz"], tgt[kept])
+    o = plyutil.read_pcl_binary(str(d / "tgt_f_outliers.ply"))
+    assert len(o) + len(f) == len(tgt)
+    # normals
+    t3 = str(d / "tgt_n.ply")
+    rc, out, err = run("normal_estimation", "-i", t2, "-o", t3, "-n", "20")
+    assert rc == 0, err
+    nrm, curv = api.normals(tgt[kept], 20, ctx=ctx)
+    n = plyutil.read_pcl_binary(t3)
+    assert np.array_equal(n["normal"], nrm) and np.array_equal(n["curvature"], curv)
+    assert np.array_equal(n["rgb"], np.full((len(kept), 3), 128, np.uint8))
+    rc, _, _ = run("normal_estimation", "-i", t2, "-o", str(d / "tgt_nr.ply"), "-n", "20", "-r")
+    assert np.array_equal(plyutil.read_pcl_binary(str(d / "tgt_nr.ply"))["normal"], -nrm)
+    # fine registration (reference behaviour: point-to-point) + accumulated + matrix file
+    reg, acc, mat = str(d / "reg.ply"), str(d / "acc.ply"), str(d / "T.txt")
+    rc, out, err = run("fine_registration", "-i", s, "-t", t3, "-o", reg, "-a", acc, "--distance_threshold", "0.02",
+                       "--matrix_file", mat)
+    assert rc == 0, err
+    lines = out.strip().split("\n")
+    assert lines[0] == f"Loaded {len(src)} data points from {s}"
+    assert lines[1] == f"Loaded {len(kept)} data points from {t3}"
+    assert lines[2] in ("Has converged: True", "Has converged: False") and lines[3].startswith("Score: ")
+    g = api.icp_align(src, tgt[kept], 0.02, 50, want_registered=True, ctx=ctx)
+    M = np.array([[float(v) for v in ln.split()] for ln in lines[4:8]])
+    assert np.allclose(M, g["transformation"], rtol=2e-5, atol=1e-7)       # printed with 6 significant digits
+    assert abs(float(lines[3].split()[1]) - g["fitness"]) <= 1e-5 * g["fitness"]
+    widths = {len(ln) for ln in lines[4:8]}
+    assert len(widths) == 1                                                # Eigen-style aligned columns
+    from lowcost3dreconstruction_b200 import chain
+    assert np.allclose(chain.read_matrix_file(mat), g["transformation"], atol=1e-7)
+    r = plyutil.read_pcl_binary(reg)
+    assert np.array_equal(r["xyz"], g["registered_xyz"])
+    a = plyutil.read_pcl_binary(acc)
+    assert len(a) == len(src) + len(kept) and np.array_equal(a["xyz"][len(src):], tgt[kept])
+    # point-to-plane extension
+    rc, out, err = run("fine_registration", "-i", s, "-t", t3, "-o", reg, "--distance_threshold", "0.02", "--point_to_plane")
+    assert rc == 0, err
+    # voxel grid
+    v = str(d / "vox.ply")
+    rc, out, err = run("cloud_downsampling", "-i", t3, "-o", v, "-s", "0.01")
+    assert rc == 0 and "Cloud after filtering: " in out
+    from lowcost3dreconstruction_b200._capi import HostCloud
+    gv = api.voxel_grid(HostCloud(tgt[kept], normal=nrm, curvature=curv,
+                                  rgba=np.full(len(kept), 0xff808080, np.uint32)), 0.01, ctx=ctx)
+    pv = plyutil.read_pcl_binary(v)
+    assert np.array_equal(pv["xyz"], gv["xyz"]) and np.array_equal(pv["rgb"], np.full((len(pv), 3), 128, np.uint8))
