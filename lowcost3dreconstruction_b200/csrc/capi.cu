@@ -172,6 +172,8 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     ctx->scratch[kScrMisc2].ensure(sizeof(SearchStats) * (p->max_iterations + 1));
     cfg.stats = ctx->scratch[kScrMisc2].as<SearchStats>();
     LC3D_CUDA(cudaMemsetAsync(cfg.stats, 0, sizeof(SearchStats) * (p->max_iterations + 1), st));
+    for (int it = 0; it <= p->max_iterations; ++it)
+      LC3D_CUDA(cudaMemsetAsync(&cfg.stats[it].c[11], 0xff, 8, st));
   }
   int32_t* d_dump_idx = nullptr;
   float* d_dump_d2 = nullptr;
@@ -248,7 +250,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     for (int it = 0; it < h_state->iter; ++it)
       std::fprintf(stderr,
                    "[lc3d stats] it %2d searched %7llu prev-seed %7llu probe %7llu borrowed %6llu walked %7llu "
-                   "fallback %6llu | warp cand-iters %9llu rows %8llu | warp cycles avg %llu max %llu, max batch %llu\n",
+                   "fallback %6llu | warp cand-iters %9llu rows %8llu | ns: search %llu, final reduce %llu, solve %llu\n",
                    it, hs[it].c[0], hs[it].c[1], hs[it].c[2], hs[it].c[3], hs[it].c[4], hs[it].c[5],
                    hs[it].c[6], hs[it].c[7], hs[it].c[8], hs[it].c[9], hs[it].c[10]);
   }

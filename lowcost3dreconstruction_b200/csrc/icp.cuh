@@ -18,7 +18,10 @@
 
 namespace lc3d {
 
-constexpr int kIcpThreads = 256;
+#ifndef LC3D_ICP_THREADS
+#define LC3D_ICP_THREADS 256
+#endif
+constexpr int kIcpThreads = LC3D_ICP_THREADS;
 constexpr int kNvP2P = 17;     // sum s(3) sum d(3) sum d s^T(9) sum d2(1) count(1)
 constexpr int kNvP2Plane = 29; // JtJ upper(21) Jtr(6) sum d2(1) count(1)
 
@@ -390,6 +393,11 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   const int iter = s_flags[1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   SearchStats* stats = cfg.stats ? cfg.stats + iter : nullptr;
+  if (stats && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    atomicMin(&stats->c[11], t0);
+  }
   double acc = 0.0;  // lane L: total of estimator value L
   {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -488,11 +496,20 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   __syncthreads();
   if (s_ticket != (unsigned)(nblk - 1)) return;
   __threadfence();
+  unsigned long long t1 = 0, t2 = 0, t3 = 0;
+  if (stats && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
   last_block_reduce<NV>(partials, nblk, red);
   __syncthreads();
   if (threadIdx.x == 0) {
     st->ticket = 0;
+    if (stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
     icp_solve_and_test<MODE>(st, cfg, red);
+    if (stats) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3));
+      stats->c[8] = t1 - stats->c[11];  // ns until the last block took its ticket
+      stats->c[9] = t2 - t1;            // ns in the final cross-block reduce
+      stats->c[10] = t3 - t2;           // ns in solve + convergence test
+    }
   }
 }
 

@@ -27,15 +27,20 @@ struct Best {
   int oi;    // original index of that target point (tie-break key)
 };
 
+// (d2, original index) packed so that one unsigned 64-bit compare orders candidates by
+// distance, ties by lower index (d2 >= 0, so the float bit pattern is monotonic).
+__device__ __forceinline__ unsigned long long pack_key(float d2, int oi) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)oi;
+}
+
 __device__ __forceinline__ void consider(const float4 p, int j, float qx, float qy, float qz,
                                          Best& b) {
-  float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-  int oi = __float_as_int(p.w);
-  if (d2 < b.d2 || (d2 == b.d2 && oi < b.oi)) {
-    b.d2 = d2;
-    b.j = j;
-    b.oi = oi;
-  }
+  const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+  const int oi = __float_as_int(p.w);
+  const bool better = pack_key(d2, oi) < pack_key(b.d2, b.oi);
+  b.d2 = better ? d2 : b.d2;
+  b.j = better ? j : b.j;
+  b.oi = better ? oi : b.oi;
 }
 
 __device__ __forceinline__ void scan_run(const float4* __restrict__ pts, uint32_t s, uint32_t e,
@@ -270,15 +275,7 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
         *n_rows += 1;
         *n_cand += e - s;
       }
-      for (uint32_t j = s; j < e; ++j) {
-        const float4 p = __ldg(&g.pts[j]);
-        const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-        const int oi = __float_as_int(p.w);
-        const bool better = d2 < b.d2 || (d2 == b.d2 && oi < b.oi);
-        b.d2 = better ? d2 : b.d2;
-        b.j = better ? (int)j : b.j;
-        b.oi = better ? oi : b.oi;
-      }
+      for (uint32_t j = s; j < e; ++j) consider(__ldg(&g.pts[j]), (int)j, qx, qy, qz, b);
     }
   }
 }
