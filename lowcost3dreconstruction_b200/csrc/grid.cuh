@@ -100,13 +100,36 @@ __global__ void __launch_bounds__(256) bbox_reduce(const float4* __restrict__ p,
     }
     cnt += __shfl_down_sync(0xffffffffu, cnt, o2);
   }
-  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+  // block combine in shared memory, then 7 atomics per BLOCK (not per warp)
+  __shared__ float s_lo[8][3], s_hi[8][3];
+  __shared__ uint32_t s_cnt[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      atomicMin(&o->lo[d], f2ord(lo[d]));
-      atomicMax(&o->hi[d], f2ord(hi[d]));
+      s_lo[w][d] = lo[d];
+      s_hi[w][d] = hi[d];
     }
-    atomicAdd(&o->count, cnt);
+    s_cnt[w] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int ww = 1; ww < (int)(blockDim.x >> 5); ++ww) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = fminf(lo[d], s_lo[ww][d]);
+        hi[d] = fmaxf(hi[d], s_hi[ww][d]);
+      }
+      cnt += s_cnt[ww];
+    }
+    if (cnt > 0) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        atomicMin(&o->lo[d], f2ord(lo[d]));
+        atomicMax(&o->hi[d], f2ord(hi[d]));
+      }
+      atomicAdd(&o->count, cnt);
+    }
   }
 }
 
@@ -218,7 +241,7 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   ctx->scratch[kScrBBox].ensure(sizeof(BBoxOut) + 16);
   BBoxOut* d_bb = ctx->scratch[kScrBBox].as<BBoxOut>();
   LC3D_LAUNCH(ctx, bbox_init, 1, 32, 0, d_bb);
-  int nb = std::min(div_up(n, 256), ctx->num_sms * 8);
+  int nb = std::min(div_up(n, 256), ctx->num_sms * 2);
   LC3D_LAUNCH(ctx, bbox_reduce, nb, 256, 0, xyz, n, d_bb);
   BBoxOut bb;
   LC3D_CUDA(cudaMemcpyAsync(&bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, st));

@@ -292,9 +292,10 @@ __device__ __forceinline__ void last_block_reduce(const double* __restrict__ par
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   for (int v = w; v < NV; v += nwarps) {
-    const volatile double* row = partials + (size_t)v * nblk;
+    const double* row = partials + (size_t)v * nblk;
     double s = 0.0;
-    for (int b = lane; b < nblk; b += 32) s += row[b];
+#pragma unroll 8
+    for (int b = lane; b < nblk; b += 32) s += __ldcg(row + b);  // L2 loads, independent: pipelined
     s = warp_sum(s);
     if (lane == 0) out_smem[v] = s;
   }
@@ -490,9 +491,11 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   }
   // ---- last block: reduce, solve, test convergence ---------------------------------
   __shared__ unsigned s_ticket;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&st->ticket, 1u);
+  }
   __syncthreads();
   if (s_ticket != (unsigned)(nblk - 1)) return;
   __threadfence();
@@ -551,9 +554,11 @@ __global__ void __launch_bounds__(kIcpThreads)
     partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
   }
   __shared__ unsigned s_ticket;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket2, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&st->ticket2, 1u);
+  }
   __syncthreads();
   if (s_ticket != (unsigned)(nblk - 1)) return;
   __threadfence();

@@ -409,17 +409,19 @@ __global__ void __launch_bounds__(256)
     partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
   }
   __shared__ unsigned s_ticket;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_ticket = atomicAdd(&st->ticket, 1u);
+  }
   __syncthreads();
   if (s_ticket != (unsigned)(nblk - 1)) return;
   __threadfence();
   {
     for (int v = w; v < 3; v += 8) {
-      const volatile double* row = partials + (size_t)v * nblk;
+      const double* row = partials + (size_t)v * nblk;
       double t = 0.0;
-      for (int b = lane; b < nblk; b += 32) t += row[b];
+      for (int b = lane; b < nblk; b += 32) t += __ldcg(row + b);
       t = warp_sum(t);
       if (lane == 0) red[v] = t;
     }

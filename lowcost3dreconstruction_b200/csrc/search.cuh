@@ -356,9 +356,12 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
       stat_add(stats, 7, mr);
     }
   }
+  int last_j = -1;  // most recent ring-search result: a good seed for the next lane (Morton
+                    // neighbours), it bounds that lane's search ball from the start
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
+    if (lane == src && last_j >= 0) consider(__ldg(&g.pts[last_j]), last_j, qx, qy, qz, b);
     Best wb;
     wb.d2 = __shfl_sync(full, b.d2, src);
     wb.j = __shfl_sync(full, b.j, src);
@@ -368,6 +371,7 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
     const float wz = __shfl_sync(full, qz, src);
     nn_phase2_warp(g, wx, wy, wz, wb);
     if (lane == src) b = wb;
+    if (wb.j >= 0) last_j = wb.j;
   }
   return b;
 }
