@@ -194,7 +194,16 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     for (auto& e : iter_ev) LC3D_CUDA(cudaEventCreate(&e));
     LC3D_CUDA(cudaEventRecord(iter_ev[0], st));
   }
-  for (int it = 0; it < p->max_iterations; ++it) {
+  // The loop runs on the device (solve + convergence test in the kernel); the host only stops
+  // ENQUEUEING: launches go out in chunks of kChunk, after each chunk the `done` flag is
+  // copied to pinned memory asynchronously, and the host looks at chunk c's flag only after
+  // chunk c+1 is already queued — no bubble, no per-iteration round trip, and far fewer no-op
+  // launches than enqueueing all max_iterations up front.
+  const int kChunk = want_stats ? p->max_iterations : 4;
+  ctx->pinned[1].ensure(sizeof(int) * (size_t)(p->max_iterations / kChunk + 2));
+  int* h_done = ctx->pinned[1].as<int>();
+  cudaEvent_t chunk_ev[2] = {ctx->chunk.a, ctx->chunk.b};
+  auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
     if (p->mode == LC3D_ICP_POINT_TO_PLANE)
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state,
@@ -202,6 +211,22 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     else
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT>, nblk, kIcpThreads, 0, d_state,
                   cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+  };
+  {
+    int it = 0, chunk = 0;
+    int pending = -1;  // chunk whose flag has been requested but not yet inspected
+    while (it < p->max_iterations) {
+      const int end = std::min(it + kChunk, p->max_iterations);
+      for (; it < end; ++it) launch_one(it);
+      h_done[chunk] = 0;
+      LC3D_CUDA(cudaMemcpyAsync(&h_done[chunk], &d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LC3D_CUDA(cudaEventRecord(chunk_ev[chunk & 1], st));
+      if (pending >= 0) {
+        LC3D_CUDA(cudaEventSynchronize(chunk_ev[pending & 1]));
+        if (h_done[pending]) break;
+      }
+      pending = chunk++;
+    }
   }
   if (want_stats) LC3D_CUDA(cudaEventRecord(iter_ev[p->max_iterations], st));
   ctx->tm[2].stop(st);
@@ -325,6 +350,7 @@ int lc3d_create(int device, void* stream, lc3d_ctx** out) {
       ctx->own_stream = true;
     }
     for (auto& t : ctx->tm) t.init();
+    ctx->chunk.init();
     ctx->grid = new Grid;
     *out = ctx;
     return LC3D_OK;
@@ -349,6 +375,7 @@ void lc3d_destroy(lc3d_ctx* ctx) {
     delete ctx->grid;
   }
   for (auto& t : ctx->tm) t.destroy();
+  ctx->chunk.destroy();
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

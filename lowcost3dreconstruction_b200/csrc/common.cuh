@@ -165,6 +165,7 @@ struct lc3d_ctx {
   lc3d::DevBuf scratch[32];  // grow-only scratch arena, slots named by the users
   lc3d::PinnedBuf pinned[2];
   lc3d::Timer tm[6];
+  lc3d::Timer chunk;  // two events used to poll the ICP loop's done flag
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
 };
