@@ -136,10 +136,12 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));
   IcpState* d_state = ctx->scratch[kScrState].as<IcpState>();
-  const int nblk_fit = std::max(1, div_up(n, kIcpThreads));
-  const int nblk = nblk_fit;
-  ctx->scratch[kScrPartials].ensure((size_t)kNvP2Plane * std::max(nblk, nblk_fit) * 8);
+  const int nblk_fit = std::max(1, div_up(n, 256));
+  const int nblk = std::max(1, div_up(n, kIcpThreads));
+  const int nwarps_icp = nblk * (kIcpThreads / 32);
+  ctx->scratch[kScrPartials].ensure((size_t)32 * std::max(nwarps_icp, nblk_fit) * 8 + 32 * 8);
   double* partials = ctx->scratch[kScrPartials].as<double>();
+  double* reduced = partials + (size_t)32 * std::max(nwarps_icp, nblk_fit);
   IcpConfig cfg;
   cfg.gate = gate_from_distance(p->max_correspondence_distance);
   if (std::isinf(cfg.gate)) {
@@ -205,12 +207,17 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   cudaEvent_t chunk_ev[2] = {ctx->chunk.a, ctx->chunk.b};
   auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
-    if (p->mode == LC3D_ICP_POINT_TO_PLANE)
+    if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state,
                   cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
-    else
+      LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, 256, 0, d_state, cfg, partials,
+                  nwarps_icp, reduced);
+    } else {
       LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT>, nblk, kIcpThreads, 0, d_state,
                   cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, 256, 0, d_state, cfg, partials,
+                  nwarps_icp, reduced);
+    }
   };
   {
     int it = 0, chunk = 0;
@@ -233,7 +240,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- getFitnessScore ----
   ctx->tm[3].start(st);
   if (p->compute_fitness)
-    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kIcpThreads, 0, d_state, G.v, X0, Mj, n, partials);
+    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kFitThreads, 0, d_state, G.v, X0, Mj, n, partials);
   ctx->tm[3].stop(st);
   // ---- results ----
   ctx->tm[4].start(st);

@@ -19,9 +19,10 @@
 namespace lc3d {
 
 #ifndef LC3D_ICP_THREADS
-#define LC3D_ICP_THREADS 256
+#define LC3D_ICP_THREADS 128
 #endif
 constexpr int kIcpThreads = LC3D_ICP_THREADS;
+constexpr int kFitThreads = 256;
 constexpr int kNvP2P = 17;     // sum s(3) sum d(3) sum d s^T(9) sum d2(1) count(1)
 constexpr int kNvP2Plane = 29; // JtJ upper(21) Jtr(6) sum d2(1) count(1)
 
@@ -356,11 +357,10 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
   return 0.0;
 }
 
-// One ICP iteration.  X: working copy of the source (float4, Morton order, w = original
-// index), transformed in place.  One thread per source point; the 32 estimator sums of a warp
-// are reduced with one butterfly reduce-scatter (lane L ends up with value L), combined per
-// block in a fixed order, written as one partial row per block, and the last block to finish
-// reduces the rows and solves.
+// One ICP iteration = this kernel + icp_solve_kernel.  X: working copy of the source (float4,
+// Morton order, w = original index), transformed in place.  One thread per source point; the
+// 32 estimator sums of a warp are reduced with one butterfly reduce-scatter (lane L ends up
+// with value L) and written as one partial row per warp.
 //
 // Per-query memory across iterations (temporal coherence):
 //   Mj[i]  : sorted-target position of the previous match (seed: its distance is an exact
@@ -371,7 +371,7 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
 // Searches run against an extended gate (r + margin)^2 so that rejected queries learn a
 // slack; a correspondence is emitted iff d2 <= gate exactly as PCL does.
 #ifndef LC3D_ICP_MINBLOCKS
-#define LC3D_ICP_MINBLOCKS 3
+#define LC3D_ICP_MINBLOCKS 6
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
@@ -380,8 +380,6 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
                          double* __restrict__ partials, int32_t* __restrict__ dump_idx,
                          float* __restrict__ dump_d2) {
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
-  __shared__ double warp_part[kIcpThreads / 32][32];
-  __shared__ double red[NV];
   __shared__ float sT[16];
   __shared__ int s_flags[2];
   if (threadIdx.x == 0) {
@@ -479,50 +477,60 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
       }
     }
   }
-  // ---- block combine (fixed order) -> one partial row per block -----------------------
-  warp_part[w][lane] = acc;
-  __syncthreads();
-  const int nblk = gridDim.x;
-  if (threadIdx.x < NV) {
-    double s = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += warp_part[ww][threadIdx.x];
-    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = s;
-  }
-  // ---- last block: reduce, solve, test convergence ---------------------------------
+  // ---- one partial row per WARP (value-major), no block-level epilogue: warps retire
+  // independently, so small blocks are cheap and the hardware scheduler balances the load
+  const int warp_global = blockIdx.x * (kIcpThreads / 32) + w;
+  const int nwarps = gridDim.x * (kIcpThreads / 32);
+  if (lane < NV) partials[(size_t)lane * nwarps + warp_global] = acc;
+}
+
+// Second kernel of an iteration: block v reduces estimator value v over all warp rows in a
+// fixed order (deterministic), the last block to finish (atomic ticket) solves, composes the
+// pose and runs the convergence test.  grid = NV blocks.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    icp_solve_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const double* __restrict__ partials,
+                     int nwarps, double* __restrict__ reduced) {
+  constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  __shared__ double sm[256];
   __shared__ unsigned s_ticket;
+  if (st->done) return;
+  const int v = blockIdx.x;
+  const double* row = partials + (size_t)v * nwarps;
+  double s = 0.0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < nwarps; i += 256) s += __ldcg(row + i);
+  sm[threadIdx.x] = s;
   __syncthreads();
+#pragma unroll
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
+    reduced[v] = sm[0];
     __threadfence();
     s_ticket = atomicAdd(&st->ticket, 1u);
   }
   __syncthreads();
-  if (s_ticket != (unsigned)(nblk - 1)) return;
-  __threadfence();
-  unsigned long long t1 = 0, t2 = 0, t3 = 0;
-  if (stats && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-  last_block_reduce<NV>(partials, nblk, red);
-  __syncthreads();
+  if (s_ticket != (unsigned)(NV - 1)) return;
   if (threadIdx.x == 0) {
+    __threadfence();
+    double red[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[k] = __ldcg(reduced + k);
     st->ticket = 0;
-    if (stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
     icp_solve_and_test<MODE>(st, cfg, red);
-    if (stats) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3));
-      stats->c[8] = t1 - stats->c[11];  // ns until the last block took its ticket
-      stats->c[9] = t2 - t1;            // ns in the final cross-block reduce
-      stats->c[10] = t3 - t2;           // ns in solve + convergence test
-    }
   }
 }
 
 // ---- getFitnessScore (fine_registration.cpp:126) --------------------------
 // transformPointCloud(*input_, tmp, final_transformation_) then the unbounded 1-NN of every
 // point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
-__global__ void __launch_bounds__(kIcpThreads)
+__global__ void __launch_bounds__(kFitThreads)
     icp_fitness_kernel(IcpState* __restrict__ st, const GridDev g, const float4* __restrict__ src0,
                        const int* __restrict__ Mj, int n, double* __restrict__ partials) {
-  __shared__ double wsum[kIcpThreads / 32], wcnt[kIcpThreads / 32];
+  __shared__ double wsum[kFitThreads / 32], wcnt[kFitThreads / 32];
   __shared__ float sT[16];
   __shared__ double red[2];
   if (threadIdx.x < 16) sT[threadIdx.x] = st->Tfinal[threadIdx.x];
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(kIcpThreads)
   const int nblk = gridDim.x;
   if (threadIdx.x < 2) {
     double t = 0.0;
-    for (int ww = 0; ww < kIcpThreads / 32; ++ww) t += threadIdx.x == 0 ? wsum[ww] : wcnt[ww];
+    for (int ww = 0; ww < kFitThreads / 32; ++ww) t += threadIdx.x == 0 ? wsum[ww] : wcnt[ww];
     partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
   }
   __shared__ unsigned s_ticket;

@@ -15,7 +15,7 @@ import tempfile
 
 rep, rx, idx = sys.argv[1], sys.argv[2], int(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-so = sys.argv[5] if len(sys.argv) > 5 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+so = os.path.abspath(sys.argv[5]) if len(sys.argv) > 5 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                         "lowcost3dreconstruction_b200", "csrc", "liblc3d.so")
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f"::regex:{rx}:{idx}"],
                      capture_output=True, text=True).stdout
