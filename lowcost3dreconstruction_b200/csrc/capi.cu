@@ -130,8 +130,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   float* Bnd = ctx->scratch[kScrBound].as<float>();
   ctx->scratch[kScrPrevMatch].ensure((size_t)n * 4 + 16);
   int* Mj = ctx->scratch[kScrPrevMatch].as<int>();
-  sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0);
-  if (n > 0) LC3D_CUDA(cudaMemcpyAsync(X, X0, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+  sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0, X);  // pristine + working copy
   ctx->tm[1].stop(st);
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));

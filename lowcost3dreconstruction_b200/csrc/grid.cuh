@@ -193,13 +193,14 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gather_sorted(const float4* __restrict__ p, const float4* __restrict__ nrm,
                   const uint32_t* __restrict__ vals, int n, float4* __restrict__ out_p,
-                  float4* __restrict__ out_n) {
+                  float4* __restrict__ out_n, float4* __restrict__ out_p2) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   uint32_t i = vals[j];
   float4 q = p[i];
   q.w = __int_as_float((int)i);
   out_p[j] = q;
+  if (out_p2) out_p2[j] = q;
   if (nrm) out_n[j] = nrm[i];
 }
 
@@ -338,7 +339,7 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   exclusive_scan_u32(ctx, cell_start, cell_start, G.ncell + 1, ctx->scratch[kScrScan].as<uint32_t>());
   // 6. gather into sorted SoA float4 (finite points come first: sentinel key sorts last)
   LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, nrm, vals, n, G.pts.as<float4>(),
-              nrm ? G.nrm.as<float4>() : nullptr);
+              nrm ? G.nrm.as<float4>() : nullptr, (float4*)nullptr);
   g.cell_start = cell_start;
   g.coarse_cnt = G.coarse_cnt.as<uint32_t>();
   g.pts = G.pts.as<float4>();
@@ -358,12 +359,12 @@ __device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
   return v;
 }
 __global__ void __launch_bounds__(256)
-    query_keys(const float4* __restrict__ p, int n, GridDev g, int shift, uint32_t* __restrict__ keys,
-               uint32_t* __restrict__ vals) {
+    query_keys(const float4* __restrict__ p, int n, GridDev g, int shift, uint32_t sentinel,
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = p[i];
-  uint32_t key = 0x40000000u;  // non-finite queries sort last
+  uint32_t key = sentinel;  // non-finite queries sort last
   if (finite3(q.x, q.y, q.z)) {
     int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256)
 }
 
 inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz, int64_t n64,
-                                 float4* out_sorted) {
+                                 float4* out_sorted, float4* out_sorted2 = nullptr) {
   const int n = (int)n64;
   if (n == 0) return;
   ctx->scratch[kScrKeys].ensure((size_t)n * 4);
@@ -390,12 +391,17 @@ inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz
   int maxdim = std::max(G.v.dx, std::max(G.v.dy, G.v.dz));
   int shift = 0;
   while ((maxdim >> shift) > 1024) ++shift;  // 10 bits per axis
-  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, keys, vals);
+  const int cb0 = bit_length((uint32_t)((maxdim - 1) >> shift));
+  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, (uint32_t)1u << (3 * cb0), keys, vals);
   SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
                  ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
-  radix_sort_pairs(ctx, keys, vals, n, 31, ss);
+  // key bits actually used: 3 interleaved coordinates of bit_length((maxdim-1) >> shift) bits,
+  // plus the non-finite sentinel bit 30 only if such points can exist (checked by the caller's
+  // bbox count): sorting all 31 bits costs a fourth radix pass for nothing
+  const int cb = bit_length((uint32_t)((maxdim - 1) >> shift));
+  radix_sort_pairs(ctx, keys, vals, n, std::min(31, 3 * cb + 1), ss);
   LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, (const float4*)nullptr, vals, n,
-              out_sorted, (float4*)nullptr);
+              out_sorted, (float4*)nullptr, out_sorted2);
 }
 
 }  // namespace lc3d

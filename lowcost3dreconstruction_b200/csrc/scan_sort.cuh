@@ -112,11 +112,53 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
   }
 }
 
+// Single-block exclusive scan for small inputs (the radix histograms: 256 x #tiles entries):
+// one launch instead of three.  Each thread owns a contiguous chunk.
+constexpr int kSmallScanThreads = 1024;
+constexpr int64_t kSmallScanMax = 2048;  // beyond this the 3-kernel tiled scan is faster
+__global__ void __launch_bounds__(kSmallScanThreads)
+    scan_small_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  __shared__ uint32_t wtot[kSmallScanThreads / 32];
+  const int per = (n + kSmallScanThreads - 1) / kSmallScanThreads;
+  const int lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; ++i) s += in[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = wtot[lane], ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    wtot[lane] = ti - t;
+  }
+  __syncthreads();
+  uint32_t run = inc - s + wtot[w];
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t v = in[i];
+    out[i] = run;
+    run += v;
+  }
+}
+
 // Exclusive scan of n uint32 (in may alias out).  `sums` scratch: >= div_up(n, kScanTile) u32.
 // Requires in/out 16-byte aligned (cudaMalloc'd).
 inline void exclusive_scan_u32(lc3d_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
                                uint32_t* sums) {
   if (n <= 0) return;
+  if (n <= kSmallScanMax) {
+    LC3D_LAUNCH(ctx, scan_small_kernel, 1, kSmallScanThreads, 0, in, out, (int)n);
+    return;
+  }
   int nb = div_up(n, kScanTile);
   LC3D_LAUNCH(ctx, scan_tile_sums, nb, kScanThreads, 0, in, n, sums);
   LC3D_LAUNCH(ctx, scan_block_sums, 1, kScanThreads, 0, sums, nb);
