@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of include/lc3d.h over the CUDA kernels.  No CPU fallback.
 #include <cfloat>
 #include <cmath>
+#include <functional>
 #include <limits>
 
 #include "common.cuh"
@@ -19,7 +20,7 @@ thread_local std::string g_create_error;
 
 // scratch slots beyond the grid builder's
 enum {
-  kScrRawA = kScrGridEnd, kScrRawB, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
+  kScrRawA = kScrGridEnd, kScrRawB, kScrRawC, kScrRawD, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
   kScrOutB, kScrDumpIdx, kScrDumpD2, kScrBound, kScrPrevMatch, kScrMisc, kScrMisc2, kScrMisc3, kScrEnd
 };
 static_assert(kScrEnd <= 32, "scratch slots");
@@ -45,52 +46,72 @@ __global__ void __launch_bounds__(256)
 }
 
 // Copies n records of `rec` bytes at `stride` from host memory into a device raw buffer
-// and returns the device pointer + the stride to use there.
+// (on stream `cs`) and returns the device pointer.
 const unsigned char* stage_raw(lc3d_ctx* ctx, DevBuf& buf, const void* host, int64_t stride,
-                               int64_t n, int rec) {
+                               int64_t n, int rec, cudaStream_t cs = nullptr) {
   if (n == 0) return nullptr;
   size_t bytes = (size_t)(n - 1) * stride + rec;
-  buf.ensure(bytes + 16);
-  LC3D_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  buf.ensure(bytes + 64);
+  LC3D_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, cs ? cs : ctx->stream));
   return buf.as<unsigned char>();
 }
 
-void upload_cloud(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals) {
+// An upload in flight: the raw strided bytes are copied on a (possibly separate) copy stream;
+// the unpack into SoA float4 happens later on the compute stream.
+struct PendingUpload {
+  const lc3d_cloud* h = nullptr;
+  lc3d_dcloud* d = nullptr;
+  const unsigned char* raw_xyz = nullptr;
+  const unsigned char* raw_nrm = nullptr;
+  cudaEvent_t ready = nullptr;  // recorded on the copy stream after the last byte, or null
+};
+
+PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals, DevBuf& raw_a,
+                           DevBuf& raw_b, cudaStream_t cs, cudaEvent_t ready) {
+  PendingUpload pu;
+  pu.h = h;
+  pu.d = d;
   const int64_t n = h->n;
   d->n = n;
   d->has_normal = false;
-  if (n == 0) return;
+  if (n == 0) return pu;
   if (n > (int64_t)INT32_MAX / 2) throw CudaError{"cloud too large (n must be < 2^30)"};
   if (!h->xyz || h->xyz_stride < 12) throw CudaError{"cloud.xyz is NULL or xyz_stride < 12"};
   d->xyz.ensure((size_t)n * 16);
-  const unsigned char* raw = stage_raw(ctx, ctx->scratch[kScrRawA], h->xyz, h->xyz_stride, n, 12);
-  LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, raw, h->xyz_stride, (int)n, 1.0f,
-              (const unsigned char*)nullptr, (int64_t)0, d->xyz.as<float4>());
   if (want_normals && h->normal) {
     if (h->normal_stride < 12) throw CudaError{"normal_stride < 12"};
     d->normal.ensure((size_t)n * 16);
-    const unsigned char* rawn;
-    // same AoS block as xyz (PCL 48-byte points)?  then the staged copy already has them
-    const ptrdiff_t off = (const char*)h->normal - (const char*)h->xyz;
-    if (h->normal_stride == h->xyz_stride && off >= 0 && off + 12 <= h->xyz_stride) {
-      // the raw copy covered (n-1)*stride + 12 bytes from xyz; normals of the last record
-      // may lie beyond it, so stage the tail explicitly
-      size_t have = (size_t)(n - 1) * h->xyz_stride + 12;
-      size_t need = (size_t)(n - 1) * h->xyz_stride + off + 12;
-      if (need > have) {
-        ctx->scratch[kScrRawA].ensure(need + 16);  // no-op: ensure() over-allocates by >= 256 B
-        LC3D_CUDA(cudaMemcpyAsync(ctx->scratch[kScrRawA].as<unsigned char>() + have,
-                                  (const char*)h->xyz + have, need - have, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-      }
-      rawn = ctx->scratch[kScrRawA].as<unsigned char>() + off;
-    } else {
-      rawn = stage_raw(ctx, ctx->scratch[kScrRawB], h->normal, h->normal_stride, n, 12);
-    }
-    LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, rawn, h->normal_stride, (int)n, 0.0f,
-                (const unsigned char*)nullptr, (int64_t)0, d->normal.as<float4>());
-    d->has_normal = true;
   }
+  // same AoS block as xyz (PCL 48-byte points)?  then one staged copy carries both
+  const ptrdiff_t off = h->normal ? (const char*)h->normal - (const char*)h->xyz : -1;
+  const bool same_block = want_normals && h->normal && h->normal_stride == h->xyz_stride && off >= 0 &&
+                          off + 12 <= h->xyz_stride;
+  pu.raw_xyz = stage_raw(ctx, raw_a, h->xyz, h->xyz_stride, n, same_block ? (int)off + 12 : 12, cs);
+  if (want_normals && h->normal)
+    pu.raw_nrm = same_block ? pu.raw_xyz + off : stage_raw(ctx, raw_b, h->normal, h->normal_stride, n, 12, cs);
+  if (ready) {
+    LC3D_CUDA(cudaEventRecord(ready, cs ? cs : ctx->stream));
+    pu.ready = ready;
+  }
+  return pu;
+}
+
+void upload_finish(lc3d_ctx* ctx, const PendingUpload& pu) {
+  const int64_t n = pu.h->n;
+  if (n == 0) return;
+  if (pu.ready) LC3D_CUDA(cudaStreamWaitEvent(ctx->stream, pu.ready, 0));
+  LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_xyz, pu.h->xyz_stride, (int)n, 1.0f,
+              (const unsigned char*)nullptr, (int64_t)0, pu.d->xyz.as<float4>());
+  if (pu.raw_nrm) {
+    LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_nrm, pu.h->normal_stride, (int)n, 0.0f,
+                (const unsigned char*)nullptr, (int64_t)0, pu.d->normal.as<float4>());
+    pu.d->has_normal = true;
+  }
+}
+
+void upload_cloud(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals) {
+  upload_finish(ctx, upload_begin(ctx, h, d, want_normals, ctx->scratch[kScrRawA], ctx->scratch[kScrRawB],
+                                  nullptr, nullptr));
 }
 
 float gate_from_distance(double max_dist) {
@@ -108,8 +129,13 @@ double cell_factor_env() {
   return f > 0.1 ? f : 2.0;
 }
 
+// before_source: called after the target index is built and before the source is first touched
+// (the host-buffer path finishes the source upload there, so that copy overlaps the build).
+// overlap_download: move the registered cloud to the host on the copy stream while
+// getFitnessScore runs.
 void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, const lc3d_icp_params* p,
-             lc3d_icp_result* res, const lc3d_icp_outputs* out) {
+             lc3d_icp_result* res, const lc3d_icp_outputs* out,
+             const std::function<void()>& before_source = nullptr, bool overlap_download = false) {
   cudaStream_t st = ctx->stream;
   const int n = (int)src->n;
   if (p->max_iterations <= 0) throw CudaError{"max_iterations needs to be greater than zero."};
@@ -122,6 +148,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   Grid& G = *ctx->grid;
   grid_build(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr,
              tgt->n, cell_factor_env());
+  if (before_source) before_source();
   ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
   ctx->scratch[kScrSrcWork].ensure((size_t)n * 16 + 16);
   float4* X0 = ctx->scratch[kScrSrcSorted].as<float4>();
@@ -236,6 +263,27 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   }
   if (want_stats) LC3D_CUDA(cudaEventRecord(iter_ev[p->max_iterations], st));
   ctx->tm[2].stop(st);
+  // ---- registered cloud (fine_registration.cpp:121 output) ----
+  cudaStream_t ds = st;  // stream the registered cloud is downloaded on
+  const bool want_reg = out && out->registered_xyz && n > 0;
+  if (want_reg) {
+    ctx->scratch[kScrOutA].ensure((size_t)n * 12);
+    const bool wn = out->registered_normal && src->has_normal;
+    if (wn) ctx->scratch[kScrOutB].ensure((size_t)n * 12);
+    LC3D_LAUNCH(ctx, transform_kernel, div_up(n, 256), 256, 0, d_state->Tfinal,
+                src->xyz.as<float4>(), wn ? src->normal.as<float4>() : nullptr, n,
+                ctx->scratch[kScrOutA].as<float>(), wn ? ctx->scratch[kScrOutB].as<float>() : nullptr);
+    if (overlap_download && ctx->copy_stream) {
+      LC3D_CUDA(cudaEventRecord(ctx->ev_copy[2], st));
+      LC3D_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
+      ds = ctx->copy_stream;
+    }
+    LC3D_CUDA(cudaMemcpyAsync(out->registered_xyz, ctx->scratch[kScrOutA].p, (size_t)n * 12,
+                              cudaMemcpyDeviceToHost, ds));
+    if (wn)
+      LC3D_CUDA(cudaMemcpyAsync(out->registered_normal, ctx->scratch[kScrOutB].p, (size_t)n * 12,
+                                cudaMemcpyDeviceToHost, ds));
+  }
   // ---- getFitnessScore ----
   ctx->tm[3].start(st);
   if (p->compute_fitness)
@@ -246,19 +294,6 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->pinned[0].ensure(sizeof(IcpState));
   IcpState* h_state = ctx->pinned[0].as<IcpState>();
   LC3D_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
-  if (out && out->registered_xyz && n > 0) {
-    ctx->scratch[kScrOutA].ensure((size_t)n * 12);
-    const bool wn = out->registered_normal && src->has_normal;
-    if (wn) ctx->scratch[kScrOutB].ensure((size_t)n * 12);
-    LC3D_LAUNCH(ctx, transform_kernel, div_up(n, 256), 256, 0, d_state->Tfinal,
-                src->xyz.as<float4>(), wn ? src->normal.as<float4>() : nullptr, n,
-                ctx->scratch[kScrOutA].as<float>(), wn ? ctx->scratch[kScrOutB].as<float>() : nullptr);
-    LC3D_CUDA(cudaMemcpyAsync(out->registered_xyz, ctx->scratch[kScrOutA].p, (size_t)n * 12,
-                              cudaMemcpyDeviceToHost, st));
-    if (wn)
-      LC3D_CUDA(cudaMemcpyAsync(out->registered_normal, ctx->scratch[kScrOutB].p, (size_t)n * 12,
-                                cudaMemcpyDeviceToHost, st));
-  }
   if (dump) {
     if (out->corr_index)
       LC3D_CUDA(cudaMemcpyAsync(out->corr_index, d_dump_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -268,6 +303,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->tm[4].stop(st);
   ctx->tm[5].stop(st);
   LC3D_CUDA(cudaStreamSynchronize(st));
+  if (ds != st) LC3D_CUDA(cudaStreamSynchronize(ds));
   if (want_stats) {
     std::vector<SearchStats> hs(p->max_iterations);
     LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * p->max_iterations, cudaMemcpyDeviceToHost));
@@ -357,6 +393,8 @@ int lc3d_create(int device, void* stream, lc3d_ctx** out) {
     }
     for (auto& t : ctx->tm) t.init();
     ctx->chunk.init();
+    LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev_copy) LC3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->grid = new Grid;
     *out = ctx;
     return LC3D_OK;
@@ -382,6 +420,9 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   }
   for (auto& t : ctx->tm) t.destroy();
   ctx->chunk.destroy();
+  for (auto& e : ctx->ev_copy)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -440,10 +481,16 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
     ctx->tm[5].start(ctx->stream);
     ctx->tm[0].start(ctx->stream);
     const bool need_src_normals = outputs && outputs->registered_normal;
-    upload_cloud(ctx, source, &tc.a, need_src_normals);
-    upload_cloud(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE);
+    // all four host->device copies go out on the copy stream right away; the compute stream
+    // waits for the target only, builds the index while the source is still in flight
+    cudaStream_t cs = ctx->copy_stream;
+    const PendingUpload pt = upload_begin(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE,
+                                          ctx->scratch[kScrRawA], ctx->scratch[kScrRawB], cs, ctx->ev_copy[0]);
+    const PendingUpload ps = upload_begin(ctx, source, &tc.a, need_src_normals, ctx->scratch[kScrRawC],
+                                          ctx->scratch[kScrRawD], cs, ctx->ev_copy[1]);
+    upload_finish(ctx, pt);
     ctx->tm[0].stop(ctx->stream);
-    icp_run(ctx, &tc.a, &tc.b, params, result, outputs);
+    icp_run(ctx, &tc.a, &tc.b, params, result, outputs, [&] { upload_finish(ctx, ps); }, true);
     result->ms_upload = ctx->tm[0].ms();
   });
 }

@@ -166,6 +166,8 @@ struct lc3d_ctx {
   lc3d::PinnedBuf pinned[2];
   lc3d::Timer tm[6];
   lc3d::Timer chunk;  // two events used to poll the ICP loop's done flag
+  cudaStream_t copy_stream = nullptr;  // H2D / D2H of the host-buffer entry points (overlaps compute)
+  cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
 };
