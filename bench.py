@@ -240,17 +240,18 @@ def main():
     def pinned(a):
         t_ = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t_, t_.numpy()
-    keep = [pinned(x) for x in (src, n_s, tgt, n_t)]
+    keep = [pinned(x) for x in (src, n_s, tgt, n_t, np.empty_like(src), np.empty_like(src))]
     Sp = HostCloud(keep[0][1], normal=keep[1][1])
     Tp = HostCloud(keep[2][1], normal=keep[3][1])
+    reg_out = (keep[4][1], keep[5][1])  # pinned result buffers: registered xyz + normals
     for _ in range(2):
-        api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, want_registered=True, ctx=ctx)
+        api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
     e_iters, e_t = 0, 0.0
     for _ in range(max(3, min(args.steps, 10))):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r = api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, want_registered=True, ctx=ctx)
+        r = api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
         e_t += time.perf_counter() - t0
         e_iters += r["iterations"]
     e = torch.tensor([e_t, float(e_iters)], dtype=torch.float64, device=dev)
@@ -274,7 +275,9 @@ def main():
     alg_bytes = 64.0 * S.n  # whole point-to-plane iteration = 64 B per source point
     achieved = alg_bytes / t_iter_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "icp_iteration_kernel<point-to-plane>",
+                # dram__bytes_read+write per launch from profiles/r01_icp_iteration_ncu_full.csv (ncu --set
+                # full, caches flushed per replay): 19.3 MB = the algorithmic bytes, i.e. no DRAM re-reads
+                "traffic": 19.3e6, "kernel": "icp_iteration_kernel<point-to-plane>",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_iter_s * 1e6,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"}
 

@@ -113,10 +113,11 @@ def _result_dict(r: IcpResult) -> dict:
 
 def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, transformation_epsilon=1e-9,
               euclidean_fitness_epsilon=1e-3, mode=POINT_TO_POINT, compute_fitness=True, dump_iteration=-1,
-              want_registered=False, ctx: Context | None = None) -> dict:
+              want_registered=False, ctx: Context | None = None, registered_out=None) -> dict:
     """pcl::IterativeClosestPoint align + getFinalTransformation + hasConverged +
     getFitnessScore (fine_registration.cpp:105-126).  src/tgt: arrays (n,3), HostCloud, or
-    DeviceCloud (both resident)."""
+    DeviceCloud (both resident).  registered_out: optional (xyz, normal) float32 (n,3) arrays to
+    receive the registered cloud (e.g. pinned memory: the download is then a true async DMA)."""
     ctx = ctx or default_context()
     p = IcpParams(float(max_correspondence_distance), float(transformation_epsilon),
                   float(euclidean_fitness_epsilon), int(max_iterations), int(mode), int(bool(compute_fitness)),
@@ -133,7 +134,16 @@ def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, tran
         out["corr_dist2"] = np.empty(n, dtype=np.float32)
         o.corr_index = out["corr_index"].ctypes.data
         o.corr_dist2 = out["corr_dist2"].ctypes.data
-    if want_registered:
+    if registered_out is not None:
+        rx, rn = registered_out
+        assert rx.dtype == np.float32 and rx.shape == (n, 3) and rx.flags.c_contiguous
+        out["registered_xyz"] = rx
+        o.registered_xyz = rx.ctypes.data
+        if rn is not None and (resident or src.normal is not None):
+            assert rn.dtype == np.float32 and rn.shape == (n, 3) and rn.flags.c_contiguous
+            out["registered_normal"] = rn
+            o.registered_normal = rn.ctypes.data
+    elif want_registered:
         out["registered_xyz"] = np.empty((n, 3), dtype=np.float32)
         o.registered_xyz = out["registered_xyz"].ctypes.data
         if resident or src.normal is not None:
