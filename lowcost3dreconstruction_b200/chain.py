@@ -3,7 +3,7 @@
 The reference chains the turntable views pairwise (scripts/alignment.sh:106-113: view i is
 registered against view i-1 and the transform is applied to all later views, i.e. cumulative
 composition; the fine-alignment step at :123-126 is the TODO this fills).  Pairs share no
-state, so pair p (view p -> view p-1) goes to rank p % world, every rank aligns its pairs on
+state, so the pairs are split into contiguous blocks, one per rank, every rank aligns its pairs on
 its own GPU, and ONLY the per-pair records (4x4 matrix, fitness, iterations, flags: 20
 doubles) are exchanged — one small all-reduce over NCCL/NVLink (gloo in CPU tests).  Rank 0
 composes G_0 = I, G_p = G_{p-1} . T_p in float64 and writes `transform -t`-readable matrix
@@ -19,8 +19,13 @@ RECORD = 20  # 16 matrix entries, fitness, iterations, converged, state
 
 
 def shard_pairs(n_pairs: int, world: int, rank: int) -> list[int]:
-    """Pairs are numbered 1..n_pairs (pair p registers view p onto view p-1)."""
-    return [p for p in range(1, n_pairs + 1) if (p - 1) % world == rank]
+    """Pairs are numbered 1..n_pairs (pair p registers view p onto view p-1).  Each rank gets a
+    CONTIGUOUS block (sizes differ by at most one): consecutive pairs share a view, so a rank
+    loads / preprocesses only len(block)+1 views instead of 2*len(block)."""
+    base, extra = divmod(n_pairs, world)
+    start = rank * base + min(rank, extra)
+    size = base + (1 if rank < extra else 0)
+    return list(range(start + 1, start + size + 1))
 
 
 def compose_chain(pair_transforms: Sequence[np.ndarray]) -> list[np.ndarray]:
