@@ -334,3 +334,23 @@ def test_transform_bit_exact(ctx, pair_normals):
     ox, on = orc.transform(src, T)
     gx, gn = api.transform(src, T, ctx=ctx)
     assert np.array_equal(gx, ox) and np.array_equal(gn, on)
+
+
+def test_empty_and_tiny_clouds(ctx):
+    e = np.zeros((0, 3), np.float32)
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    few = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    for s, t in ((e, few), (few, e), (one, one), (e, e)):
+        g = api.icp_align(s, t, 0.5, 5, ctx=ctx)
+        o = orc.icp_align(s, t, 0.5, 5)
+        assert g["state"] == o["state"] == 5 and not g["converged"] and g["iterations"] == 0
+        assert np.array_equal(g["transformation"], np.eye(4, dtype=np.float32))
+    g = api.icp_align(few + np.float32(0.01), few, 0.5, 20, want_registered=True, ctx=ctx)
+    o = orc.icp_align(few + np.float32(0.01), few, 0.5, 20, want_registered=True)
+    assert g["iterations"] == o["iterations"] and np.abs(g["transformation"] - o["transformation"]).max() < 1e-5
+    assert api.voxel_grid(e, 0.1, ctx=ctx)["xyz"].shape == (0, 3)
+    assert len(api.sor(e, 5, 1.0, ctx=ctx)[0]) == 0
+    idx, d2 = api.nn(e, few, ctx=ctx)
+    assert idx.tolist() == [-1] * 4
+    nrm, curv = api.normals(few[:2], 5, ctx=ctx)
+    assert np.isnan(nrm).all()
