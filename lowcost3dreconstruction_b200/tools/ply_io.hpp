@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -71,6 +72,92 @@ inline double read_bin(const unsigned char* p, Type t) {
     case F64: { double v; std::memcpy(&v, p, 8); return v; }
     default: return 0;
   }
+}
+
+// Fast decimal -> double for the ASCII body: exact (correctly rounded) on the Clinger fast path
+// (<= 15 significant digits, |exp10| <= 22: mantissa and power of ten are exact doubles, one
+// rounded multiply/divide), strtod for everything else (long mantissas, nan/inf, hex...).
+// Returns the position after the token, or nullptr at end of input / on a malformed token.
+inline const char* parse_number(const char* p, const char* end, double* out) {
+  while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+  if (p >= end) return nullptr;
+  const char* start = p;
+  bool neg = false;
+  if (*p == '-' || *p == '+') {
+    neg = *p == '-';
+    ++p;
+  }
+  uint64_t mant = 0;
+  int digits = 0, frac = 0;
+  bool any = false;
+  while (p < end && *p >= '0' && *p <= '9') {
+    if (digits < 18) {
+      mant = mant * 10 + (uint64_t)(*p - '0');
+      if (mant) ++digits;
+    } else {
+      --frac;  // dropped digit: fall back below
+      digits = 99;
+    }
+    any = true;
+    ++p;
+  }
+  if (p < end && *p == '.') {
+    ++p;
+    while (p < end && *p >= '0' && *p <= '9') {
+      if (digits < 18) {
+        mant = mant * 10 + (uint64_t)(*p - '0');
+        if (mant) ++digits;
+        ++frac;
+      } else {
+        digits = 99;
+      }
+      any = true;
+      ++p;
+    }
+  }
+  int exp10 = 0;
+  bool fast = any && digits <= 15;
+  if (any && p < end && (*p == 'e' || *p == 'E')) {
+    const char* q = p + 1;
+    bool eneg = false;
+    if (q < end && (*q == '-' || *q == '+')) {
+      eneg = *q == '-';
+      ++q;
+    }
+    if (q < end && *q >= '0' && *q <= '9') {
+      int e = 0;
+      while (q < end && *q >= '0' && *q <= '9') {
+        if (e < 10000) e = e * 10 + (*q - '0');
+        ++q;
+      }
+      exp10 = eneg ? -e : e;
+      p = q;
+    }
+  }
+  const bool token_end = p >= end || *p == ' ' || *p == '\t' || *p == '\n' || *p == '\r';
+  static const double kPow10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                  1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const int e = exp10 - frac;
+  if (fast && token_end && e >= -22 && e <= 22) {
+    double v = (double)mant;
+    v = e < 0 ? v / kPow10[-e] : v * kPow10[e];
+    *out = neg ? -v : v;
+    return p;
+  }
+  // slow path: let strtod decide (also handles nan / inf / malformed tokens)
+  const char* tok_end = start;
+  while (tok_end < end && !(*tok_end == ' ' || *tok_end == '\t' || *tok_end == '\n' || *tok_end == '\r')) ++tok_end;
+  char buf[128];
+  size_t len = (size_t)(tok_end - start);
+  if (len == 0) return nullptr;
+  if (len >= sizeof buf) len = sizeof buf - 1;
+  std::memcpy(buf, start, len);
+  buf[len] = 0;
+  char* ep = nullptr;
+  double v = std::strtod(buf, &ep);
+  if (ep == buf) v = std::nan("");  // non-numeric token
+  *out = v;
+  return tok_end;
 }
 
 struct Property {
@@ -179,6 +266,10 @@ inline int load_ply(const std::string& path, Cloud& cloud, std::string* err = nu
   }
   if (!header_done || format < 0) return fail("truncated PLY header");
   cloud = Cloud();
+  std::vector<char> ascii;
+  const char* cur = nullptr;
+  const char* ascii_end = nullptr;
+  bool ascii_loaded = false;
   for (const Element& e : elems) {
     const bool is_vertex = e.name == "vertex";
     std::vector<Slot> slots;
@@ -191,27 +282,31 @@ inline int load_ply(const std::string& path, Cloud& cloud, std::string* err = nu
     }
     if (is_vertex) cloud.points.reserve(e.count);
     if (format == 0) {
+      if (!ascii_loaded) {  // slurp the rest of the file once; tokens are parsed in memory
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos fin = in.tellg();
+        in.seekg(here);
+        ascii.resize((size_t)(fin - here));
+        in.read(ascii.data(), (std::streamsize)ascii.size());
+        cur = ascii.data();
+        ascii_end = ascii.data() + ascii.size();
+        ascii_loaded = true;
+      }
       for (size_t i = 0; i < e.count; ++i) {
         Point pt{};
         pt.w = 1.0f;
         pt.rgba = 0xff000000u;
         for (size_t k = 0; k < e.props.size(); ++k) {
           const Property& p = e.props[k];
+          double v;
           if (p.is_list) {
-            long cnt = 0;
-            if (!(in >> cnt)) return fail("truncated PLY data");
-            double skip;
+            if (!(cur = parse_number(cur, ascii_end, &v))) return fail("truncated PLY data");
+            const long cnt = (long)v;
             for (long c = 0; c < cnt; ++c)
-              if (!(in >> skip)) return fail("truncated PLY data");
+              if (!(cur = parse_number(cur, ascii_end, &v))) return fail("truncated PLY data");
           } else {
-            double v;
-            if (!(in >> v)) {
-              // non-numeric token such as "nan"
-              in.clear();
-              std::string t;
-              if (!(in >> t)) return fail("truncated PLY data");
-              v = std::nan("");
-            }
+            if (!(cur = parse_number(cur, ascii_end, &v))) return fail("truncated PLY data");
             if (is_vertex) assign(pt, slots[k], v, p.type, nullptr);
           }
         }

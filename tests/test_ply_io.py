@@ -95,3 +95,33 @@ def test_rejects_garbage(tmp_path):
     open(be, "w").write("ply\nformat binary_big_endian 1.0\nelement vertex 0\nend_header\n")
     rc, out, err = convert(be, str(tmp_path / "o.ply"))
     assert rc == 255 and "unsupported" in err
+
+
+def test_ascii_number_parser_is_exact(tmp_path):
+    """The fast ASCII parser must give the same float32 as a correctly rounded decimal->double->
+    float conversion (what PCL's iostream-based reader produces) for every token shape."""
+    rng = np.random.default_rng(3)
+    toks = ["0", "-0", "+3.", ".5", "-.25", "1e-5", "1E+2", "2.5e3", "123456789.123456789", "0.000001",
+            "-0.0000001234567890123456789", "3.4028234e38", "1.17549435e-38", "1e-45", "123456789012345678901234567890",
+            "0.1", "0.2", "0.30000000000000004", "9007199254740993", "1.7976931348623157e308", "4.9e-324",
+            "inf", "-inf", "nan", "1e400", "-1e-400"]
+    for _ in range(3000):
+        kind = rng.integers(0, 4)
+        x = rng.normal() * 10.0 ** rng.integers(-8, 9)
+        toks.append({0: "%.6f" % x, 1: "%.9g" % x, 2: "%.17g" % x, 3: "%e" % x}[int(kind)])
+    while len(toks) % 3:
+        toks.append("1")
+    vals = np.array(toks).reshape(-1, 3)
+    src, dst = str(tmp_path / "n.ply"), str(tmp_path / "o.ply")
+    with open(src, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "end_header\n" % len(vals))
+        for r in vals:
+            f.write(" ".join(r) + "\n")
+    rc, out, err = convert(src, dst)
+    assert rc == 0, err
+    got = plyutil.read_pcl_binary(dst)["xyz"].reshape(-1)
+    with np.errstate(over="ignore"):
+        want = np.array([float(t) for t in vals.reshape(-1)], dtype=np.float64).astype(np.float32)
+    assert np.array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
