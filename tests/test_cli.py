@@ -149,3 +149,38 @@ def test_pipeline_end_to_end(ply_pair, ctx):
                                   rgba=np.full(len(kept), 0xff808080, np.uint32)), 0.01, ctx=ctx)
     pv = plyutil.read_pcl_binary(v)
     assert np.array_equal(pv["xyz"], gv["xyz"]) and np.array_equal(pv["rgb"], np.full((len(pv), 3), 128, np.uint8))
+
+
+def test_chain_registration_cli_contract():
+    rc, out, err = run("chain_registration", "--help")
+    assert rc == 0 and "-n [ --num_captures ] arg" in out and "--point_to_plane" in out
+    rc, out, err = run("chain_registration")
+    assert rc == 255 and err.startswith("Correct mode of use: ")
+    rc, out, err = run("chain_registration", "-n", "3", "-d", "/nonexistent")
+    assert rc == 255 and err.strip() == "Couldn't load input point cloud: /nonexistent/0.ply"
+
+
+@pytest.mark.gpu
+def test_chain_registration_matches_python_chain(tmp_path, ctx):
+    """The in-process chain tool gives the same pair transforms / composed poses as
+    chain.register_chain over the C ABI, and writes transform -t readable matrices."""
+    from lowcost3dreconstruction_b200 import api, chain
+    n = 4
+    views = []
+    for v in range(n):
+        c = np.round(synth.kinect_view(v, step_deg=4.0, scale=0.15, backdrop="panel").astype(np.float64), 6).astype(np.float32)
+        views.append(c)
+        plyutil.write_capture_ascii(str(tmp_path / f"{v}.ply"), c)
+    out = tmp_path / "out"
+    out.mkdir()
+    rc, so, err = run("chain_registration", "-n", str(n), "-d", str(tmp_path), "-o", str(out), "--distance_threshold", "0.03")
+    assert rc == 0, err
+    ref = chain.register_chain(n, lambda v: views[v], lambda s, t: api.icp_align(s, t, 0.03, 50, ctx=ctx))
+    for i in range(1, n):
+        G = chain.read_matrix_file(str(out / f"fine_{i}.txt"))
+        assert np.allclose(G, ref["pose"][i], atol=2e-6)
+        moved = plyutil.read_pcl_binary(str(out / f"{i}.ply"))["xyz"]
+        exp, _ = api.transform(views[i], ref["pose"][i].astype(np.float32), ctx=ctx)
+        assert np.abs(moved - exp).max() < 1e-5
+    assert np.array_equal(plyutil.read_pcl_binary(str(out / "0.ply"))["xyz"], views[0])
+    assert so.count("Has converged: ") == n - 1
