@@ -123,10 +123,18 @@ float gate_from_distance(double max_dist) {
   return g;  // largest float with (double)g <= max_dist^2: "d2 > max^2" rejects exactly as PCL
 }
 
+// Cell edge in units of the estimated point spacing.  Measured optimum on B200 (profiles/
+// r01_summary.md): ~4 for the 1-NN searches of ICP (fewer, longer rows; smaller index table),
+// ~1.5 for the k-NN passes.  Overridable for experiments.
 double cell_factor_env() {
   const char* e = std::getenv("LC3D_CELL_FACTOR");
-  double f = e ? std::atof(e) : 2.0;
-  return f > 0.1 ? f : 2.0;
+  double f = e ? std::atof(e) : 4.0;
+  return f > 0.1 ? f : 4.0;
+}
+double knn_cell_factor_env() {
+  const char* e = std::getenv("LC3D_KNN_CELL_FACTOR");
+  double f = e ? std::atof(e) : 1.5;
+  return f > 0.1 ? f : 1.5;
 }
 
 // before_source: called after the target index is built and before the source is first touched
