@@ -182,6 +182,17 @@ int lc3d_sor(lc3d_ctx* ctx, const lc3d_cloud* cloud, int32_t mean_k, double stdd
              int32_t negative, int32_t* out_kept_index, int64_t* out_count, float* out_mean_dist,
              double out_stats[3]);
 
+/* ------------------------------------------------------- accumulate_clouds --- */
+
+/* Replaces the per-target-point pcl::CropBox (negative) loop of
+ * pcl_tools/accumulate_clouds.cpp:100-111: a source point is dropped iff
+ * some target point t has it inside the axis-aligned box [t - radius, t + radius] (corners
+ * rounded to float, bounds inclusive, as CropBox evaluates them); non-finite source points are
+ * dropped.  O(N) on the grid index instead of O(N*M).  out_kept_index: caller-allocated
+ * source->n entries, receives the surviving source indices in source order. */
+int lc3d_box_dedup(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* target, double radius,
+                   int32_t* out_kept_index, int64_t* out_count);
+
 /* ------------------------------------------------------------ transform ----- */
 
 /* pcl::transformPointCloudWithNormals (pcl_tools/transform.cpp:84-90; SURVEY §8f

@@ -231,6 +231,18 @@ def voxel_grid(cloud, leaf, ctx: Context | None = None) -> dict:
                 curvature=None if curv is None else curv[:m].copy(), voxel_of_point=vox[: c.n])
 
 
+def box_dedup(src, tgt, radius: float, ctx: Context | None = None) -> np.ndarray:
+    """accumulate_clouds.cpp:100-111: indices of the source points that lie in no target point's
+    +/- radius box (the points the tool keeps before its SOR pass)."""
+    ctx = ctx or default_context()
+    s, t = _hc(src), _hc(tgt)
+    kept = np.empty(max(s.n, 1), dtype=np.int32)
+    cnt = C.c_int64(0)
+    ctx._check(ctx._lib.lc3d_box_dedup(ctx._h, s.ref(), t.ref(), float(radius), kept.ctypes.data,
+                                       C.byref(cnt)), "lc3d_box_dedup")
+    return kept[: cnt.value].copy()
+
+
 def transform(cloud, T, ctx: Context | None = None):
     ctx = ctx or default_context()
     c = _hc(cloud)

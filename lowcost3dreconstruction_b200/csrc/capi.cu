@@ -5,6 +5,7 @@
 #include <limits>
 
 #include "common.cuh"
+#include "dedup.cuh"
 #include "grid.cuh"
 #include "icp.cuh"
 #include "knn.cuh"

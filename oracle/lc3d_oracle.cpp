@@ -1167,6 +1167,35 @@ void orc_transform(const lc3d_cloud* c, const float T16[16], float* out_xyz, flo
   }
 }
 
+// accumulate_clouds.cpp:100-111: for every target point t, pcl::CropBox (negative) drops the
+// source points inside the axis-aligned box [t - r, t + r]; the box corners are computed as
+// (float)((double)t.x -/+ r) and the test is min <= p <= max per component (inclusive), so a
+// source point survives iff NO target point has it inside its box.  Non-finite source points
+// are dropped by CropBox.  Literal O(N*M) restatement (the order of the survivors is the
+// source order, as CropBox preserves it).
+int orc_box_dedup(const lc3d_cloud* src, const lc3d_cloud* tgt, double radius, int32_t* out_kept,
+                  int64_t* out_count) {
+  std::vector<char> alive(src->n, 1);
+  for (int64_t i = 0; i < src->n; ++i)
+    if (!finite3(xyz_at(src, i))) alive[i] = 0;
+  for (int64_t j = 0; j < tgt->n; ++j) {
+    const float* t = xyz_at(tgt, j);
+    const float lo[3] = {(float)((double)t[0] - radius), (float)((double)t[1] - radius), (float)((double)t[2] - radius)};
+    const float hi[3] = {(float)((double)t[0] + radius), (float)((double)t[1] + radius), (float)((double)t[2] + radius)};
+    for (int64_t i = 0; i < src->n; ++i) {
+      if (!alive[i]) continue;
+      const float* p = xyz_at(src, i);
+      const bool outside = p[0] < lo[0] || p[1] < lo[1] || p[2] < lo[2] || p[0] > hi[0] || p[1] > hi[1] || p[2] > hi[2];
+      if (!outside) alive[i] = 0;
+    }
+  }
+  int64_t c = 0;
+  for (int64_t i = 0; i < src->n; ++i)
+    if (alive[i]) out_kept[c++] = (int32_t)i;
+  *out_count = c;
+  return 0;
+}
+
 // Exposed for tests of the oracle's own building blocks.
 void orc_kabsch_rotation(const double S[9], double R[9]) { kabsch_rotation(S, R); }
 void orc_eigen33(const float C[9], float* eigenvalue, float v[3]) { eigen33_smallest(C, eigenvalue, v); }

@@ -55,6 +55,8 @@ def load():
     lib.orc_sor.restype = C.c_int
     lib.orc_voxel_grid.argtypes = [cp, C.POINTER(C.c_float), vp, vp, vp, vp, vp, C.POINTER(i64)]
     lib.orc_voxel_grid.restype = C.c_int
+    lib.orc_box_dedup.argtypes = [cp, cp, f64, vp, C.POINTER(i64)]
+    lib.orc_box_dedup.restype = C.c_int
     lib.orc_transform.argtypes = [cp, C.POINTER(C.c_float), vp, vp]
     lib.orc_transform.restype = None
     lib.orc_kabsch_rotation.argtypes = [C.POINTER(f64), C.POINTER(f64)]
@@ -179,6 +181,14 @@ def voxel_grid(cloud, leaf):
     return dict(xyz=xyz[:m].copy(), normal=None if nrm is None else nrm[:m].copy(),
                 rgba=None if rgba is None else rgba[:m].copy(),
                 curvature=None if curv is None else curv[:m].copy(), voxel_of_point=vox, overflow=rc == 1)
+
+
+def box_dedup(src, tgt, radius: float):
+    s, t = _hc(src), _hc(tgt)
+    kept = np.empty(max(s.n, 1), dtype=np.int32)
+    cnt = C.c_int64(0)
+    load().orc_box_dedup(s.ref(), t.ref(), float(radius), kept.ctypes.data, C.byref(cnt))
+    return kept[: cnt.value].copy()
 
 
 def transform(cloud, T):

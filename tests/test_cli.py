@@ -11,7 +11,7 @@ from tests import plyutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "lowcost3dreconstruction_b200", "tools", "bin")
-TOOLS = ["fine_registration", "normal_estimation", "cloud_downsampling", "outlier_removal"]
+TOOLS = ["fine_registration", "normal_estimation", "cloud_downsampling", "outlier_removal", "accumulate_clouds"]
 
 
 def run(tool, *args):
@@ -48,7 +48,7 @@ def test_missing_mandatory_options(tool):
     rc, out, err = run(tool)
     assert rc == 255  # return -1
     assert err.startswith("Correct mode of use: ") and "-i input.ply" in err and "-o output.ply [opts]" in err
-    if tool == "fine_registration":
+    if tool in ("fine_registration", "accumulate_clouds"):
         assert "-t target.ply" in err
 
 
@@ -184,3 +184,37 @@ def test_chain_registration_matches_python_chain(tmp_path, ctx):
         assert np.abs(moved - exp).max() < 1e-5
     assert np.array_equal(plyutil.read_pcl_binary(str(out / "0.ply"))["xyz"], views[0])
     assert so.count("Has converged: ") == n - 1
+
+
+def test_accumulate_clouds_all_needs_no_gpu(tmp_path):
+    """--all (the only mode scripts/integration.sh:98 uses) is a plain concatenation."""
+    a, b, o = str(tmp_path / "a.ply"), str(tmp_path / "b.ply"), str(tmp_path / "o.ply")
+    xa, xb = np.arange(9.0).reshape(3, 3), np.arange(12.0).reshape(4, 3) + 100
+    plyutil.write_capture_ascii(a, xa)
+    plyutil.write_capture_ascii(b, xb)
+    rc, out, err = run("accumulate_clouds", "--all", "-i", a, "-t", b, "-o", o)
+    assert rc == 0, err
+    assert out.startswith(f"Loaded 3 data points from {a}\nLoaded 4 data points from {b}\nCloud before accumulate: ")
+    assert "Cloud after accumulate: \nheader: seq: 0 stamp: 0 frame_id: \n\npoints[]: 7\n" in out
+    pts = plyutil.read_pcl_binary(o)
+    assert np.array_equal(pts["xyz"], np.concatenate([xb, xa]).astype(np.float32))  # target first, then source
+    rc, _, err = run("accumulate_clouds", "-i", a, "-t", "/nonexistent.ply", "-o", o)
+    assert rc == 255 and err.strip() == "Couldn't load target point cloud: /nonexistent.ply"
+
+
+@pytest.mark.gpu
+def test_accumulate_clouds_dedup(ply_pair, ctx):
+    from lowcost3dreconstruction_b200 import api
+    d, src, tgt = ply_pair
+    o = str(d / "acc_dedup.ply")
+    rc, out, err = run("accumulate_clouds", "-i", str(d / "src.ply"), "-t", str(d / "tgt.ply"), "-o", o,
+                       "--radius", "0.004", "--clean_neighbors", "10", "--dev_mult", "2.0", "--negative")
+    assert rc == 0, err
+    kept = api.box_dedup(src, tgt, 0.004, ctx=ctx)
+    kept2, _, _ = api.sor(src[kept], 10, 2.0, ctx=ctx)
+    want = src[kept][kept2]
+    pts = plyutil.read_pcl_binary(o)
+    assert len(pts) == len(tgt) + len(want)
+    assert np.array_equal(pts["xyz"][: len(tgt)], tgt) and np.array_equal(pts["xyz"][len(tgt):], want)
+    assert np.array_equal(plyutil.read_pcl_binary(str(d / "acc_dedup_negative.ply"))["xyz"], want)
+    assert "|----|----|" in out  # the progress banner the reference prints on stdout

@@ -354,3 +354,17 @@ def test_empty_and_tiny_clouds(ctx):
     assert idx.tolist() == [-1] * 4
     nrm, curv = api.normals(few[:2], 5, ctx=ctx)
     assert np.isnan(nrm).all()
+
+
+@pytest.mark.parametrize("radius", [0.002, 0.01, 0.05])
+def test_box_dedup_bit_exact(ctx, pair, radius):
+    """accumulate_clouds.cpp:100-111 de-dup: kept-index list identical to the O(N*M) restatement."""
+    src, tgt = pair
+    rng = np.random.default_rng(2)
+    s = src[rng.choice(len(src), 4000, replace=False)].copy()
+    s[:50] = tgt[:50] + np.float32(radius)            # on the inclusive box face
+    s[50] = np.nan
+    t = tgt[rng.choice(len(tgt), 6000, replace=False)]
+    assert np.array_equal(api.box_dedup(s, t, radius, ctx=ctx), orc.box_dedup(s, t, radius))
+    assert len(api.box_dedup(s, np.zeros((0, 3), np.float32), radius, ctx=ctx)) == len(s) - 1   # only the NaN goes
+    assert len(api.box_dedup(tgt, tgt, radius, ctx=ctx)) == 0                                    # everything is redundant

@@ -223,3 +223,18 @@ def test_oracle_reproduces_golden_fixtures():
     assert np.array_equal(kept, g["sor_kept"]) and np.array_equal(md, g["sor_mean"])
     v = orc.voxel_grid(T, 0.02)
     assert np.array_equal(v["voxel_of_point"], g["vox_of_point"]) and np.array_equal(v["xyz"], g["vox_xyz"])
+
+
+def test_box_dedup_against_numpy():
+    rng = np.random.default_rng(4)
+    tgt = rng.uniform(0, 1, (600, 3)).astype(np.float32)
+    src = rng.uniform(-0.2, 1.2, (900, 3)).astype(np.float32)
+    src[10] = np.nan
+    src[20:25] = tgt[5:10] + np.float32(0.03)       # exactly on a box face for r = 0.03 (inclusive bound)
+    for r in (0.03, 0.1, 0.0):
+        kept = orc.box_dedup(src, tgt, r)
+        lo = (tgt.astype(np.float64) - r).astype(np.float32)
+        hi = (tgt.astype(np.float64) + r).astype(np.float32)
+        inside = ((src[:, None, :] >= lo[None]) & (src[:, None, :] <= hi[None])).all(-1).any(-1)
+        want = np.flatnonzero(~inside & np.isfinite(src).all(1))
+        assert np.array_equal(kept, want)
