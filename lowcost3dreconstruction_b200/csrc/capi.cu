@@ -132,6 +132,12 @@ double cell_factor_env() {
   double f = e ? std::atof(e) : 4.0;
   return f > 0.1 ? f : 4.0;
 }
+// x subdivision of the 1-NN index cells (power of two): rows stay few, runs clip tightly.
+int xsub_env() {
+  const char* e = std::getenv("LC3D_XSUB");
+  int x = e ? std::atoi(e) : 4;
+  return x >= 1 && x <= 16 ? x : 4;
+}
 double knn_cell_factor_env() {
   const char* e = std::getenv("LC3D_KNN_CELL_FACTOR");
   double f = e ? std::atof(e) : 1.5;
@@ -156,7 +162,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->tm[1].start(st);
   Grid& G = *ctx->grid;
   grid_build(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr,
-             tgt->n, cell_factor_env());
+             tgt->n, cell_factor_env(), 0.0, xsub_env());
   if (before_source) before_source();
   ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
   ctx->scratch[kScrSrcWork].ensure((size_t)n * 16 + 16);
@@ -316,7 +322,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   if (want_stats) {
     std::vector<SearchStats> hs(p->max_iterations);
     LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * p->max_iterations, cudaMemcpyDeviceToHost));
-    std::fprintf(stderr, "[lc3d stats] cell %.5f dims %dx%dx%d n_src %d\n", G.v.c, G.v.dx, G.v.dy, G.v.dz, n);
+    std::fprintf(stderr, "[lc3d stats] cell %.5f xsub %d dims %dx%dx%d n_src %d\n", G.v.c, G.v.xs, G.v.dx, G.v.dy, G.v.dz, n);
     for (int it = 0; it < h_state->iter + 1 && it < p->max_iterations; ++it) {
       float ms = 0;
       cudaEventElapsedTime(&ms, iter_ev[it], iter_ev[it + 1]);
@@ -529,7 +535,7 @@ int lc3d_nn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, d
     const int n = (int)q->n;
     if (n == 0) return;
     Grid& G = ctx_grid(ctx);
-    grid_build(ctx, G, tc.b.xyz.as<float4>(), nullptr, tc.b.n, cell_factor_env());
+    grid_build(ctx, G, tc.b.xyz.as<float4>(), nullptr, tc.b.n, cell_factor_env(), 0.0, xsub_env());
     ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
     float4* Q = ctx->scratch[kScrSrcSorted].as<float4>();
     sort_queries_by_cell(ctx, G, q->xyz.as<float4>(), n, Q);

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256)
     const float rm = (float)radius * 1.0001f + 1e-6f * g.c;
     const float wc = rm * g.inv_c + 2.0f * kCellSlack;
     const QueryCell qc = query_cell(g, s.x, s.y, s.z);
-    const int x0 = max((int)floorf(qc.fx - wc), 0), x1 = min((int)floorf(qc.fx + wc), g.dx - 1);
+    const float wcx = wc * (float)g.xs;  // x-subcells
+    const int x0 = max((int)floorf(qc.fx - wcx), 0), x1 = min((int)floorf(qc.fx + wcx), g.dx - 1);
     const int y0 = max((int)floorf(qc.fy - wc), 0), y1 = min((int)floorf(qc.fy + wc), g.dy - 1);
     const int z0 = max((int)floorf(qc.fz - wc), 0), z1 = min((int)floorf(qc.fz + wc), g.dz - 1);
     if (x0 <= x1 && y0 <= y1 && z0 <= z1) {

@@ -27,11 +27,17 @@ constexpr int kCoarseShift = 3;  // super-cell = 8^3 cells
 constexpr int kCoarse = 1 << kCoarseShift;
 constexpr float kCellSlack = 1e-3f;  // cells; covers float rounding of cell coordinates
 constexpr int kMaxDim = 2048;
+constexpr int kMaxDimX = 4096;  // x-subcells
 constexpr int64_t kMaxCells = (int64_t)1 << 26;
 
 struct GridDev {
   float ox, oy, oz;
   float c, inv_c;
+  // cells are c x c x c, except that x is subdivided `xs` (power of two) times: rows (y,z) stay
+  // few while the x-run of a row clips tightly to the search ball.  dx counts x-SUBcells,
+  // inv_cx = xs / c, inv_xs = 1 / xs.
+  float inv_cx, inv_xs;
+  int xs, xs_shift;
   int dx, dy, dz;
   int cdx, cdy, cdz;
   int n;  // finite points indexed
@@ -176,14 +182,14 @@ __global__ void __launch_bounds__(256)
   float4 q = p[i];
   uint32_t key = ncell;
   if (finite3(q.x, q.y, q.z)) {
-    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
+    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_cx)), 0), g.dx - 1);
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
     int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
     key = (uint32_t)((iz * g.dy + iy) * g.dx + ix);
     if (cell_cnt) atomicAdd(&cell_cnt[key], 1u);
     if (coarse_cnt)
       atomicAdd(&coarse_cnt[((iz >> kCoarseShift) * g.cdy + (iy >> kCoarseShift)) * g.cdx +
-                            (ix >> kCoarseShift)],
+                            (ix >> (kCoarseShift + g.xs_shift))],
                 1u);
   }
   keys[i] = key;
@@ -220,13 +226,14 @@ enum { kScrBBox = 0, kScrProbe, kScrKeys, kScrVals, kScrKeysAlt, kScrValsAlt, kS
 // Builds the grid over `xyz` (n float4, input order).  cell_factor: cell edge in units of
 // the estimated point spacing.  min_cell > 0 forces a lower bound on the cell edge.
 inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
-                       double cell_factor, double min_cell = 0.0) {
+                       double cell_factor, double min_cell = 0.0, int xsub = 1) {
   const int n = (int)n64;
   cudaStream_t st = ctx->stream;
   G.v = GridDev{};
   if (n == 0) {
     G.v.dx = G.v.dy = G.v.dz = G.v.cdx = G.v.cdy = G.v.cdz = 1;
-    G.v.c = G.v.inv_c = 1.0f;
+    G.v.c = G.v.inv_c = G.v.inv_cx = G.v.inv_xs = 1.0f;
+    G.v.xs = 1;
     G.ncell = 1;
     G.cell_start.ensure(2 * 4);
     G.coarse_cnt.ensure(4);
@@ -288,13 +295,23 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   cell = std::max(cell, maxext / (kMaxDim - 2));
   cell = std::max(cell, 1e-30);
   int dims[3];
+  int xs = 1, xs_shift = 0;
+  while (xs * 2 <= xsub && xs < 16) {
+    xs *= 2;
+    ++xs_shift;
+  }
   for (int iter = 0; iter < 64; ++iter) {
     int64_t tot = 1;
     for (int d = 0; d < 3; ++d) {
       dims[d] = (int)std::floor(ext[d] / cell) + 1;
       tot *= dims[d];
     }
-    if (tot <= kMaxCells) break;
+    // the x subdivision must keep dx within the range the cell-coordinate slack covers
+    while (xs > 1 && ((int64_t)dims[0] * xs > kMaxDimX || tot * xs > kMaxCells)) {
+      xs >>= 1;
+      --xs_shift;
+    }
+    if (tot * xs <= kMaxCells) break;
     cell *= std::cbrt((double)tot / (double)kMaxCells) * 1.02;
   }
   GridDev& g = G.v;
@@ -303,10 +320,15 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   g.oz = G.lo[2];
   g.c = (float)cell;
   g.inv_c = 1.0f / g.c;
-  g.dx = dims[0];
+  g.xs = xs;
+  g.xs_shift = xs_shift;
+  g.inv_xs = 1.0f / (float)xs;
+  g.inv_cx = g.inv_c * (float)xs;  // exact (power of two)
+  // x-subcells: every c-cell of the isotropic layout splits into xs slices
+  g.dx = dims[0] * xs;
   g.dy = dims[1];
   g.dz = dims[2];
-  g.cdx = (g.dx + kCoarse - 1) >> kCoarseShift;
+  g.cdx = (dims[0] + kCoarse - 1) >> kCoarseShift;
   g.cdy = (g.dy + kCoarse - 1) >> kCoarseShift;
   g.cdz = (g.dz + kCoarse - 1) >> kCoarseShift;
   g.n = nfinite;
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(256)
   float4 q = p[i];
   uint32_t key = sentinel;  // non-finite queries sort last
   if (finite3(q.x, q.y, q.z)) {
-    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_c)), 0), g.dx - 1);
+    int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_cx)), 0), g.dx - 1) >> g.xs_shift;
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
     int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
     key = morton_spread10((uint32_t)ix >> shift) | (morton_spread10((uint32_t)iy >> shift) << 1) |
@@ -388,7 +410,7 @@ inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz
   ctx->scratch[kScrScan].ensure(scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile)) + 64);
   uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
   uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
-  int maxdim = std::max(G.v.dx, std::max(G.v.dy, G.v.dz));
+  int maxdim = std::max(G.v.dx >> G.v.xs_shift, std::max(G.v.dy, G.v.dz));
   int shift = 0;
   while ((maxdim >> shift) > 1024) ++shift;  // 10 bits per axis
   const int cb0 = bit_length((uint32_t)((maxdim - 1) >> shift));

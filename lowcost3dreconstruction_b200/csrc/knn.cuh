@@ -88,6 +88,7 @@ __device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, 
   s.cnt = 0;
   s.thresh = kMaxKey;
   if (g.n == 0) return;
+  // the ring logic below assumes cubic cells: k-NN indices are built with xsub = 1
   const QueryCell qc = query_cell(g, qx, qy, qz);
   const float c2 = g.c * g.c * 0.9999f;
   // first ring that touches the grid (queries may lie outside it)

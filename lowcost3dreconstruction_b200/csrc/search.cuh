@@ -60,7 +60,7 @@ struct QueryCell {
 };
 __device__ __forceinline__ QueryCell query_cell(const GridDev& g, float qx, float qy, float qz) {
   QueryCell c;
-  c.fx = cell_coord(qx, g.ox, g.inv_c);
+  c.fx = cell_coord(qx, g.ox, g.inv_cx);  // in x-SUBcells
   c.fy = cell_coord(qy, g.oy, g.inv_c);
   c.fz = cell_coord(qz, g.oz, g.inv_c);
   // clamp so that int conversion and later arithmetic cannot overflow
@@ -89,7 +89,7 @@ __device__ __forceinline__ bool nn_phase1(const GridDev& g, const QueryCell& qc,
       float gz = oz ? slab_gap(qc.fz, zz, zz) : 0.0f;
       if ((gy * gy + gz * gz) * c2 > b.d2) continue;
     }
-    const int x0 = max(qc.ix - 1, 0), x1 = min(qc.ix + 1, g.dx - 1);
+    const int x0 = max(qc.ix - g.xs, 0), x1 = min(qc.ix + g.xs, g.dx - 1);
     if (x0 > x1) continue;
     const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
     const uint32_t s = __ldg(row + x0), e = __ldg(row + x1 + 1);
@@ -98,8 +98,8 @@ __device__ __forceinline__ bool nn_phase1(const GridDev& g, const QueryCell& qc,
   // Everything inside the 3x3x3 block was scanned or safely culled; any other point is
   // at least `gmin` cells away (faces of the block that lie outside the grid bound nothing).
   float gmin = 1.0e30f;
-  if (qc.ix - 1 > 0) gmin = fminf(gmin, qc.fx - (float)(qc.ix - 1));
-  if (qc.ix + 2 < g.dx) gmin = fminf(gmin, (float)(qc.ix + 2) - qc.fx);
+  if (qc.ix - g.xs > 0) gmin = fminf(gmin, (qc.fx - (float)(qc.ix - g.xs)) * g.inv_xs);
+  if (qc.ix + g.xs + 1 < g.dx) gmin = fminf(gmin, ((float)(qc.ix + g.xs + 1) - qc.fx) * g.inv_xs);
   if (qc.iy - 1 > 0) gmin = fminf(gmin, qc.fy - (float)(qc.iy - 1));
   if (qc.iy + 2 < g.dy) gmin = fminf(gmin, (float)(qc.iy + 2) - qc.fy);
   if (qc.iz - 1 > 0) gmin = fminf(gmin, qc.fz - (float)(qc.iz - 1));
@@ -122,7 +122,8 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
   const QueryCell qc = query_cell(g, qx, qy, qz);
   const float c2 = g.c * g.c * 0.9999f;
   const float inv_c2 = 1.0f / c2;
-  const int cx = qc.ix >> kCoarseShift, cy = qc.iy >> kCoarseShift, cz = qc.iz >> kCoarseShift;
+  const int xsh = kCoarseShift + g.xs_shift, kCoarseX = 1 << xsh;  // super-cell edge in x-subcells
+  const int cx = qc.ix >> xsh, cy = qc.iy >> kCoarseShift, cz = qc.iz >> kCoarseShift;
   Best lb = b;        // lane-local best
   float bd = b.d2;    // warp-uniform pruning bound (min over lanes so far)
   // first ring that can touch the grid
@@ -146,7 +147,7 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
         ccz = z0 + t / (nx * ny);
         const int ring = max(max(abs(ccx - cx), abs(ccy - cy)), abs(ccz - cz));
         if (ring == R) {
-          float gx = slab_gap(qc.fx, ccx * kCoarse, ccx * kCoarse + kCoarse - 1);
+          float gx = slab_gap(qc.fx, ccx * kCoarseX, ccx * kCoarseX + kCoarseX - 1) * g.inv_xs;
           float gy = slab_gap(qc.fy, ccy * kCoarse, ccy * kCoarse + kCoarse - 1);
           float gz = slab_gap(qc.fz, ccz * kCoarse, ccz * kCoarse + kCoarse - 1);
           if ((gx * gx + gy * gy + gz * gz) * c2 <= bd)
@@ -157,7 +158,7 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        const int bx = __shfl_sync(0xffffffffu, ccx, src) * kCoarse;
+        const int bx = __shfl_sync(0xffffffffu, ccx, src) * kCoarseX;
         const int by = __shfl_sync(0xffffffffu, ccy, src) * kCoarse;
         const int bz = __shfl_sync(0xffffffffu, ccz, src) * kCoarse;
         const float bdc = bd * inv_c2;  // bound in cells^2 (may be +inf)
@@ -169,8 +170,8 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
             const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
             const float rem = bdc - (gy * gy + gz * gz);
             if (rem >= 0.0f) {
-              const float w = sqrtf(rem) + 2.0f * kCellSlack;
-              int xa = bx, xb = min(bx + kCoarse - 1, g.dx - 1);
+              const float w = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
+              int xa = bx, xb = min(bx + kCoarseX - 1, g.dx - 1);
               // clip the row to the x-extent of the search ball (w may be +inf)
               const float fl = qc.fx - w, fh = qc.fx + w;
               if (fl > (float)xa) xa = (int)floorf(fl);
@@ -190,8 +191,8 @@ __device__ __noinline__ void nn_phase2_warp(const GridDev& g, float qx, float qy
     // super-cells that still have grid behind them
     float gmin = 1.0e30f;
     bool open = false;
-    if ((cx - R) > 0) { gmin = fminf(gmin, qc.fx - (float)((cx - R) * kCoarse)); open = true; }
-    if ((cx + R + 1) < g.cdx) { gmin = fminf(gmin, (float)((cx + R + 1) * kCoarse) - qc.fx); open = true; }
+    if ((cx - R) > 0) { gmin = fminf(gmin, (qc.fx - (float)((cx - R) * kCoarseX)) * g.inv_xs); open = true; }
+    if ((cx + R + 1) < g.cdx) { gmin = fminf(gmin, ((float)((cx + R + 1) * kCoarseX) - qc.fx) * g.inv_xs); open = true; }
     if ((cy - R) > 0) { gmin = fminf(gmin, qc.fy - (float)((cy - R) * kCoarse)); open = true; }
     if ((cy + R + 1) < g.cdy) { gmin = fminf(gmin, (float)((cy + R + 1) * kCoarse) - qc.fy); open = true; }
     if ((cz - R) > 0) { gmin = fminf(gmin, qc.fz - (float)((cz - R) * kCoarse)); open = true; }
@@ -262,7 +263,7 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
         const float gy = slab_gap(qc.fy, yy, yy);
         const float rem = b.d2 * inv_c2 - (gy * gy + gz2);
         if (rem >= 0.0f) {
-          const float wx = sqrtf(rem) + 2.0f * kCellSlack;
+          const float wx = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
           const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
           if (xa <= xb) {
             const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
