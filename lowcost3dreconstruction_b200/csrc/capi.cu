@@ -249,13 +249,21 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
     if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
-      LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state,
-                  cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      if (want_stats)
+        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk, kIcpThreads, 0, d_state,
+                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      else
+        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, 0, d_state,
+                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, 256, 0, d_state, cfg, partials,
                   nwarps_icp, reduced);
     } else {
-      LC3D_LAUNCH(ctx, icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT>, nblk, kIcpThreads, 0, d_state,
-                  cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      if (want_stats)
+        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk, kIcpThreads, 0, d_state,
+                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      else
+        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, 0, d_state,
+                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, 256, 0, d_state, cfg, partials,
                   nwarps_icp, reduced);
     }

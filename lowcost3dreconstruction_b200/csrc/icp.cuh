@@ -150,31 +150,55 @@ __device__ void kabsch_rotation_dev(const double* S, double* R) {
                      dv * U[i * 3 + 2] * W[j * 3 + 2];
 }
 
-__device__ bool solve6_dev(double* A, double* b, double* x) {
+// 6x6 Gaussian elimination with partial pivoting, fully unrolled so that the matrix lives in
+// registers (run by ONE thread on the iteration's critical path; with dynamic row indices the
+// arrays went to local memory and the solve took ~7 us).  Pivoting by conditional row swaps:
+// the pivot row is the same as with a single max search (ties aside), the other rows only
+// change places, and each row's elimination arithmetic does not depend on its position.
+__device__ __forceinline__ bool solve6_dev(double (&A)[36], double (&b)[6], double (&x)[6]) {
+  // all loops have fixed trip counts (guards instead of variable bounds) so that nvcc unrolls
+  // them completely and every A[...] index is a compile-time constant
+  bool ok = true;
+#pragma unroll
   for (int c = 0; c < 6; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < 6; ++r)
-      if (fabs(A[r * 6 + c]) > fabs(A[piv * 6 + c])) piv = r;
-    if (A[piv * 6 + c] == 0.0) return false;
-    if (piv != c) {
-      for (int k = 0; k < 6; ++k) {
-        double t = A[c * 6 + k];
-        A[c * 6 + k] = A[piv * 6 + k];
-        A[piv * 6 + k] = t;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r > c) {
+        const bool sw = fabs(A[r * 6 + c]) > fabs(A[c * 6 + c]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          if (k >= c) {
+            const double t = A[c * 6 + k], u = A[r * 6 + k];
+            A[c * 6 + k] = sw ? u : t;
+            A[r * 6 + k] = sw ? t : u;
+          }
+        }
+        const double t = b[c], u = b[r];
+        b[c] = sw ? u : t;
+        b[r] = sw ? t : u;
       }
-      double t = b[c];
-      b[c] = b[piv];
-      b[piv] = t;
     }
-    for (int r = c + 1; r < 6; ++r) {
-      double f = A[r * 6 + c] / A[c * 6 + c];
-      for (int k = c; k < 6; ++k) A[r * 6 + k] -= f * A[c * 6 + k];
-      b[r] -= f * b[c];
+    ok = ok && A[c * 6 + c] != 0.0;
+    const double piv = ok ? A[c * 6 + c] : 1.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r > c) {
+        const double f = A[r * 6 + c] / piv;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k >= c) A[r * 6 + k] -= f * A[c * 6 + k];
+        b[r] -= f * b[c];
+      }
     }
   }
-  for (int r = 5; r >= 0; --r) {
+  if (!ok) return false;
+#pragma unroll
+  for (int rr = 0; rr < 6; ++rr) {
+    const int r = 5 - rr;
     double s = b[r];
-    for (int k = r + 1; k < 6; ++k) s -= A[r * 6 + k] * x[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k > r) s -= A[r * 6 + k] * x[k];
     x[r] = s / A[r * 6 + r];
   }
   return true;
@@ -198,13 +222,15 @@ __device__ void icp_solve_and_test(IcpState* st, const IcpConfig& cfg, const dou
   for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
   if (MODE == LC3D_ICP_POINT_TO_PLANE) {
     double A[36], b[6], x[6];
-    int k = 0;
+#pragma unroll
     for (int i = 0; i < 6; ++i)
+#pragma unroll
       for (int j = i; j < 6; ++j) {
+        const int k = i * 6 - (i * (i - 1)) / 2 + (j - i);  // upper-triangle packing
         A[i * 6 + j] = v[k];
         A[j * 6 + i] = v[k];
-        ++k;
       }
+#pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = v[21 + i];
     if (solve6_dev(A, b, x)) {
       double al = x[0], be = x[1], ga = x[2];
@@ -371,11 +397,12 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
 // Searches run against an extended gate (r + margin)^2 so that rejected queries learn a
 // slack; a correspondence is emitted iff d2 <= gate exactly as PCL does.
 #ifndef LC3D_ICP_MINBLOCKS
-#define LC3D_ICP_MINBLOCKS 6
+#define LC3D_ICP_MINBLOCKS 8
 #endif
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
-    icp_iteration_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const GridDev g,
+    icp_iteration_kernel(IcpState* __restrict__ st, const __grid_constant__ IcpConfig cfg,
+                         const __grid_constant__ GridDev g,
                          float4* __restrict__ X, float* __restrict__ Bnd, int* __restrict__ Mj, int n,
                          double* __restrict__ partials, int32_t* __restrict__ dump_idx,
                          float* __restrict__ dump_d2) {
@@ -391,7 +418,9 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   if (s_flags[0]) return;
   const int iter = s_flags[1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  SearchStats* stats = cfg.stats ? cfg.stats + iter : nullptr;
+  // the statistics plumbing is compiled out of the production instantiation: the search
+  // kernel is register-bound and every live counter costs occupancy
+  SearchStats* stats = (STATS && cfg.stats) ? cfg.stats + iter : nullptr;
   if (stats && threadIdx.x == 0) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -528,7 +557,7 @@ __global__ void __launch_bounds__(256)
 // transformPointCloud(*input_, tmp, final_transformation_) then the unbounded 1-NN of every
 // point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
 __global__ void __launch_bounds__(kFitThreads)
-    icp_fitness_kernel(IcpState* __restrict__ st, const GridDev g, const float4* __restrict__ src0,
+    icp_fitness_kernel(IcpState* __restrict__ st, const __grid_constant__ GridDev g, const float4* __restrict__ src0,
                        const int* __restrict__ Mj, int n, double* __restrict__ partials) {
   __shared__ double wsum[kFitThreads / 32], wcnt[kFitThreads / 32];
   __shared__ float sT[16];
@@ -617,7 +646,7 @@ __global__ void __launch_bounds__(256)
 // Plain batched 1-NN (lc3d_nn): queries in cell-sorted order, results scattered back to
 // the original query order.
 __global__ void __launch_bounds__(256)
-    nn_kernel(const GridDev g, const float4* __restrict__ q_sorted, int n, float gate,
+    nn_kernel(const __grid_constant__ GridDev g, const float4* __restrict__ q_sorted, int n, float gate,
               int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = i < n;

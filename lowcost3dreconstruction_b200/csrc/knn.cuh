@@ -249,7 +249,7 @@ struct KnnArgs {
 };
 
 template <int CAP, int CONSUMER>
-__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const GridDev g, const KnnArgs a) {
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_constant__ GridDev g, const __grid_constant__ KnnArgs a) {
   __shared__ unsigned long long sbuf[kKnnWarps][CAP];
   __shared__ float snb[CONSUMER == kConsumeNormals ? kKnnWarps : 1][CONSUMER == kConsumeNormals ? CAP : 1][3];
   __shared__ double sdist[CONSUMER == kConsumeSor ? kKnnWarps : 1][CONSUMER == kConsumeSor ? CAP : 1];
