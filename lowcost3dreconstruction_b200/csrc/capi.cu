@@ -177,7 +177,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));
   IcpState* d_state = ctx->scratch[kScrState].as<IcpState>();
-  const int nblk_fit = std::max(1, div_up(n, 256));
+  const int nblk_fit = std::max(1, div_up(n, kFitThreads));
   const int nblk = std::max(1, div_up(n, kIcpThreads));
   const int nwarps_icp = nblk * (kIcpThreads / 32);
   ctx->scratch[kScrPartials].ensure((size_t)32 * std::max(nwarps_icp, nblk_fit) * 8 + 32 * 8);
@@ -310,7 +310,8 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- getFitnessScore ----
   ctx->tm[3].start(st);
   if (p->compute_fitness)
-    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kFitThreads, 0, d_state, G.v, X0, Mj, n, partials);
+    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kFitThreads, 0, d_state, G.v, X0, Mj, n, partials,
+                cfg.stats ? cfg.stats + p->max_iterations : (SearchStats*)nullptr);
   ctx->tm[3].stop(st);
   // ---- results ----
   ctx->tm[4].start(st);
@@ -328,8 +329,15 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   LC3D_CUDA(cudaStreamSynchronize(st));
   if (ds != st) LC3D_CUDA(cudaStreamSynchronize(ds));
   if (want_stats) {
-    std::vector<SearchStats> hs(p->max_iterations);
-    LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * p->max_iterations, cudaMemcpyDeviceToHost));
+    std::vector<SearchStats> hs(p->max_iterations + 1);
+    LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * (p->max_iterations + 1), cudaMemcpyDeviceToHost));
+    {
+      const SearchStats& f = hs[p->max_iterations];
+      std::fprintf(stderr,
+                   "[lc3d stats] fitness searched %llu prev-seed %llu probe %llu borrowed %llu walked %llu "
+                   "fallback %llu | warp cand-iters %llu rows %llu\n",
+                   f.c[0], f.c[1], f.c[2], f.c[3], f.c[4], f.c[5], f.c[6], f.c[7]);
+    }
     std::fprintf(stderr, "[lc3d stats] cell %.5f xsub %d dims %dx%dx%d n_src %d\n", G.v.c, G.v.xs, G.v.dx, G.v.dy, G.v.dz, n);
     for (int it = 0; it < h_state->iter + 1 && it < p->max_iterations; ++it) {
       float ms = 0;

@@ -82,6 +82,7 @@ __global__ void bbox_init(BBoxOut* o) {
     o->lo[0] = o->lo[1] = o->lo[2] = 0xffffffffu;
     o->hi[0] = o->hi[1] = o->hi[2] = 0u;
     o->count = 0;
+    o->pad = 0;  // receives the probe's occupied-cell count
   }
 }
 
@@ -142,11 +143,24 @@ __global__ void __launch_bounds__(256) bbox_reduce(const float4* __restrict__ p,
 // Density probe: occupancy bitmask of a 64^3 grid over the bbox; the number of occupied
 // probe cells estimates the sampled surface area and hence the point spacing.
 constexpr int kProbe = 64;
+__device__ __forceinline__ float ord2f_dev(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+// The bbox is read from device memory (written by bbox_reduce just before on the same stream),
+// so the build needs ONE host round trip (bbox + occupancy together) instead of two.
 __global__ void __launch_bounds__(256)
-    probe_mark(const float4* __restrict__ p, int n, float ox, float oy, float oz, float sx, float sy,
-               float sz, uint32_t* __restrict__ bits) {
+    probe_mark(const float4* __restrict__ p, int n, const BBoxOut* __restrict__ bb,
+               uint32_t* __restrict__ bits) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || bb->count <= 1u) return;
+  const float ox = ord2f_dev(bb->lo[0]), oy = ord2f_dev(bb->lo[1]), oz = ord2f_dev(bb->lo[2]);
+  const double ex = (double)ord2f_dev(bb->hi[0]) - (double)ox, ey = (double)ord2f_dev(bb->hi[1]) - (double)oy,
+               ez = (double)ord2f_dev(bb->hi[2]) - (double)oz;
+  const double maxext = fmax(ex, fmax(ey, ez));
+  if (!(maxext > 0.0)) return;
+  const float sx = (float)((double)kProbe / fmax(ex, maxext * 1e-6));
+  const float sy = (float)((double)kProbe / fmax(ey, maxext * 1e-6));
+  const float sz = (float)((double)kProbe / fmax(ez, maxext * 1e-6));
   float4 q = p[i];
   if (!finite3(q.x, q.y, q.z)) return;
   int ix = min(max((int)((q.x - ox) * sx), 0), kProbe - 1);
@@ -251,6 +265,13 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   LC3D_LAUNCH(ctx, bbox_init, 1, 32, 0, d_bb);
   int nb = std::min(div_up(n, 256), ctx->num_sms * 2);
   LC3D_LAUNCH(ctx, bbox_reduce, nb, 256, 0, xyz, n, d_bb);
+  // 2. density probe (64^3 occupancy over the bbox, bbox read on the device), then ONE round trip
+  const int nwords = kProbe * kProbe * kProbe / 32;
+  ctx->scratch[kScrProbe].ensure(nwords * 4 + 16);
+  uint32_t* bits = ctx->scratch[kScrProbe].as<uint32_t>();
+  LC3D_CUDA(cudaMemsetAsync(bits, 0, nwords * 4 + 16, st));
+  LC3D_LAUNCH(ctx, probe_mark, div_up(n, 256), 256, 0, xyz, n, d_bb, bits);
+  LC3D_LAUNCH(ctx, probe_count, 32, 256, 0, bits, nwords, &d_bb->pad);
   BBoxOut bb;
   LC3D_CUDA(cudaMemcpyAsync(&bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, st));
   LC3D_CUDA(cudaStreamSynchronize(st));
@@ -269,23 +290,14 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
     ext[d] = (double)G.hi[d] - (double)G.lo[d];
     maxext = std::max(maxext, ext[d]);
   }
-  // 2. density probe -> point spacing -> cell edge
+  // point spacing (surface area ~ occupied probe cells) -> cell edge
   double cell;
   if (nfinite <= 1 || maxext <= 0) {
     cell = maxext > 0 ? maxext : 1.0;
   } else {
     double pe[3];
     for (int d = 0; d < 3; ++d) pe[d] = std::max(ext[d], maxext * 1e-6) / kProbe;
-    const int nwords = kProbe * kProbe * kProbe / 32;
-    ctx->scratch[kScrProbe].ensure(nwords * 4 + 16);
-    uint32_t* bits = ctx->scratch[kScrProbe].as<uint32_t>();
-    LC3D_CUDA(cudaMemsetAsync(bits, 0, nwords * 4 + 16, st));
-    LC3D_LAUNCH(ctx, probe_mark, div_up(n, 256), 256, 0, xyz, n, G.lo[0], G.lo[1], G.lo[2],
-                (float)(1.0 / pe[0]), (float)(1.0 / pe[1]), (float)(1.0 / pe[2]), bits);
-    LC3D_LAUNCH(ctx, probe_count, 32, 256, 0, bits, nwords, bits + nwords);
-    uint32_t occ = 0;
-    LC3D_CUDA(cudaMemcpyAsync(&occ, bits + nwords, 4, cudaMemcpyDeviceToHost, st));
-    LC3D_CUDA(cudaStreamSynchronize(st));
+    const uint32_t occ = bb.pad;
     double cell_area = std::pow(pe[0] * pe[1] * pe[2], 2.0 / 3.0);
     double area = std::max(1.0, (double)occ) * cell_area;
     double spacing = std::sqrt(area / (double)nfinite);

@@ -22,7 +22,10 @@ namespace lc3d {
 #define LC3D_ICP_THREADS 128
 #endif
 constexpr int kIcpThreads = LC3D_ICP_THREADS;
-constexpr int kFitThreads = 256;
+#ifndef LC3D_FIT_THREADS
+#define LC3D_FIT_THREADS 256
+#endif
+constexpr int kFitThreads = LC3D_FIT_THREADS;
 constexpr int kNvP2P = 17;     // sum s(3) sum d(3) sum d s^T(9) sum d2(1) count(1)
 constexpr int kNvP2Plane = 29; // JtJ upper(21) Jtr(6) sum d2(1) count(1)
 
@@ -81,62 +84,83 @@ __global__ void icp_state_init(IcpState* st) {
 // Rotation of the Umeyama / Kabsch problem for cross-covariance S (row-major 3x3):
 // S = U D V^T, R = U diag(1,1,det(U)det(V)) V^T.  One-sided (Hestenes) Jacobi on the
 // columns of S; the third left vector is u1 x u2, which folds det(U) into the product.
-__device__ void kabsch_rotation_dev(const double* S, double* R) {
+// Written with fixed trip counts and selects instead of index arrays so that A, V, U, W stay
+// in registers (the solve is one thread on the iteration's critical path).
+__device__ __forceinline__ double sel3(int o, double a0, double a1, double a2) {
+  return o == 0 ? a0 : (o == 1 ? a1 : a2);
+}
+__device__ __forceinline__ void kabsch_rotation_dev(const double* S, double* R) {
   double A[9], V[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) {
     A[i] = S[i];
     V[i] = (i % 4 == 0) ? 1.0 : 0.0;
   }
   for (int sweep = 0; sweep < 40; ++sweep) {
     bool rotated = false;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        double al = 0, be = 0, ga = 0;
-        for (int k = 0; k < 3; ++k) {
-          al += A[k * 3 + p] * A[k * 3 + p];
-          be += A[k * 3 + q] * A[k * 3 + q];
-          ga += A[k * 3 + p] * A[k * 3 + q];
-        }
-        if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
-        rotated = true;
-        double zeta = (be - al) / (2.0 * ga);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int k = 0; k < 3; ++k) {
-          double ap = A[k * 3 + p], aq = A[k * 3 + q];
-          A[k * 3 + p] = c * ap - s * aq;
-          A[k * 3 + q] = s * ap + c * aq;
-          double vp = V[k * 3 + p], vq = V[k * 3 + q];
-          V[k * 3 + p] = c * vp - s * vq;
-          V[k * 3 + q] = s * vp + c * vq;
-        }
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;  // (0,1) (0,2) (1,2)
+      double al = 0, be = 0, ga = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        al += A[k * 3 + p] * A[k * 3 + p];
+        be += A[k * 3 + q] * A[k * 3 + q];
+        ga += A[k * 3 + p] * A[k * 3 + q];
       }
+      if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+      rotated = true;
+      double zeta = (be - al) / (2.0 * ga);
+      double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double ap = A[k * 3 + p], aq = A[k * 3 + q];
+        A[k * 3 + p] = c * ap - s * aq;
+        A[k * 3 + q] = s * ap + c * aq;
+        double vp = V[k * 3 + p], vq = V[k * 3 + q];
+        V[k * 3 + p] = c * vp - s * vq;
+        V[k * 3 + q] = s * vp + c * vq;
+      }
+    }
     if (!rotated) break;
   }
-  double sg[3];
-  for (int c = 0; c < 3; ++c)
-    sg[c] = A[c] * A[c] + A[3 + c] * A[3 + c] + A[6 + c] * A[6 + c];
+  double sg0 = A[0] * A[0] + A[3] * A[3] + A[6] * A[6];
+  double sg1 = A[1] * A[1] + A[4] * A[4] + A[7] * A[7];
+  double sg2 = A[2] * A[2] + A[5] * A[5] + A[8] * A[8];
   int o0 = 0, o1 = 1, o2 = 2;  // descending singular values
-  if (sg[o0] < sg[o1]) { int t = o0; o0 = o1; o1 = t; }
-  if (sg[o1] < sg[o2]) { int t = o1; o1 = o2; o2 = t; }
-  if (sg[o0] < sg[o1]) { int t = o0; o0 = o1; o1 = t; }
+  if (sel3(o0, sg0, sg1, sg2) < sel3(o1, sg0, sg1, sg2)) { int t = o0; o0 = o1; o1 = t; }
+  if (sel3(o1, sg0, sg1, sg2) < sel3(o2, sg0, sg1, sg2)) { int t = o1; o1 = o2; o2 = t; }
+  if (sel3(o0, sg0, sg1, sg2) < sel3(o1, sg0, sg1, sg2)) { int t = o0; o0 = o1; o1 = t; }
   double U[9], W[9];
-  const int ord[3] = {o0, o1, o2};
-  for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) W[r * 3 + c] = V[r * 3 + ord[c]];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    W[r * 3 + 0] = sel3(o0, V[r * 3], V[r * 3 + 1], V[r * 3 + 2]);
+    W[r * 3 + 1] = sel3(o1, V[r * 3], V[r * 3 + 1], V[r * 3 + 2]);
+    W[r * 3 + 2] = sel3(o2, V[r * 3], V[r * 3 + 1], V[r * 3 + 2]);
+  }
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
-    double nrm = sqrt(sg[ord[c]]);
-    for (int r = 0; r < 3; ++r) U[r * 3 + c] = nrm > 0 ? A[r * 3 + ord[c]] / nrm : (r == c ? 1.0 : 0.0);
+    const int oc = c == 0 ? o0 : o1;
+    const double nrm = sqrt(sel3(oc, sg0, sg1, sg2));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double a = sel3(oc, A[r * 3], A[r * 3 + 1], A[r * 3 + 2]);
+      U[r * 3 + c] = nrm > 0 ? a / nrm : (r == c ? 1.0 : 0.0);
+    }
   }
   {
     double dot = U[0] * U[1] + U[3] * U[4] + U[6] * U[7], nrm = 0;
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
       U[r * 3 + 1] -= dot * U[r * 3 + 0];
       nrm += U[r * 3 + 1] * U[r * 3 + 1];
     }
     nrm = sqrt(nrm);
-    if (nrm > 0)
+    if (nrm > 0) {
+#pragma unroll
       for (int r = 0; r < 3; ++r) U[r * 3 + 1] /= nrm;
+    }
     U[2] = U[3] * U[7] - U[6] * U[4];
     U[5] = U[6] * U[1] - U[0] * U[7];
     U[8] = U[0] * U[4] - U[3] * U[1];
@@ -144,7 +168,9 @@ __device__ void kabsch_rotation_dev(const double* S, double* R) {
   double detW = W[0] * (W[4] * W[8] - W[5] * W[7]) - W[1] * (W[3] * W[8] - W[5] * W[6]) +
                 W[2] * (W[3] * W[7] - W[4] * W[6]);
   double dv = detW < 0 ? -1.0 : 1.0;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j)
       R[i * 3 + j] = U[i * 3 + 0] * W[j * 3 + 0] + U[i * 3 + 1] * W[j * 3 + 1] +
                      dv * U[i * 3 + 2] * W[j * 3 + 2];
@@ -558,7 +584,8 @@ __global__ void __launch_bounds__(256)
 // point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
 __global__ void __launch_bounds__(kFitThreads)
     icp_fitness_kernel(IcpState* __restrict__ st, const __grid_constant__ GridDev g, const float4* __restrict__ src0,
-                       const int* __restrict__ Mj, int n, double* __restrict__ partials) {
+                       const int* __restrict__ Mj, int n, double* __restrict__ partials,
+                       SearchStats* stats) {
   __shared__ double wsum[kFitThreads / 32], wcnt[kFitThreads / 32];
   __shared__ float sT[16];
   __shared__ double red[2];
@@ -575,7 +602,7 @@ __global__ void __launch_bounds__(kFitThreads)
   // seeded by the last iteration's matches (the final pose differs from the incremental one
   // only by float rounding), unbounded: every source point counts
   const int seed_j = (active && Mj) ? Mj[i] : -1;
-  Best b = nn_search_seeded(g, active, x, y, z, INFINITY, seed_j, nullptr);
+  Best b = nn_search_seeded(g, active, x, y, z, INFINITY, seed_j, stats);
   const bool has = active && b.j >= 0;
   double s = warp_sum(has ? (double)b.d2 : 0.0);
   unsigned any = __ballot_sync(0xffffffffu, has);
