@@ -177,7 +177,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));
   IcpState* d_state = ctx->scratch[kScrState].as<IcpState>();
-  const int nblk_fit = std::max(1, div_up(n, kFitThreads));
+  const int nblk_fit = kFitReduceBlocks;
   const int nblk = std::max(1, div_up(n, kIcpThreads));
   const int nwarps_icp = nblk * (kIcpThreads / 32);
   ctx->scratch[kScrPartials].ensure((size_t)32 * std::max(nwarps_icp, nblk_fit) * 8 + 32 * 8);
@@ -309,9 +309,21 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   }
   // ---- getFitnessScore ----
   ctx->tm[3].start(st);
-  if (p->compute_fitness)
-    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk_fit, kFitThreads, 0, d_state, G.v, X0, Mj, n, partials,
+  if (p->compute_fitness) {
+    // Bnd is dead after the loop: it becomes the per-point squared distance array
+    float* d2_all = Bnd;
+    ctx->scratch[kScrMisc3].ensure((size_t)(2 * (size_t)n + 4) * 4);
+    FitQueue fq;
+    fq.idx = ctx->scratch[kScrMisc3].as<int>();
+    fq.seed = fq.idx + n;
+    fq.count = reinterpret_cast<unsigned*>(fq.seed + n);
+    LC3D_CUDA(cudaMemsetAsync(fq.count, 0, 4, st));
+    LC3D_LAUNCH(ctx, icp_fitness_kernel, nblk, kIcpThreads, 0, d_state, G.v, X0, Mj, n, d2_all, fq,
                 cfg.stats ? cfg.stats + p->max_iterations : (SearchStats*)nullptr);
+    LC3D_LAUNCH(ctx, icp_fitness_hard_kernel, ctx->num_sms * 8, 128, 0, d_state, G.v, X0, d2_all, fq);
+    LC3D_LAUNCH(ctx, icp_fitness_reduce_kernel, kFitReduceBlocks, 256, 0, d_state, d2_all, n, partials,
+                fq.count);
+  }
   ctx->tm[3].stop(st);
   // ---- results ----
   ctx->tm[4].start(st);

@@ -581,17 +581,30 @@ __global__ void __launch_bounds__(256)
 
 // ---- getFitnessScore (fine_registration.cpp:126) --------------------------
 // transformPointCloud(*input_, tmp, final_transformation_) then the unbounded 1-NN of every
-// point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).
-__global__ void __launch_bounds__(kFitThreads)
-    icp_fitness_kernel(IcpState* __restrict__ st, const __grid_constant__ GridDev g, const float4* __restrict__ src0,
-                       const int* __restrict__ Mj, int n, double* __restrict__ partials,
-                       SearchStats* stats) {
-  __shared__ double wsum[kFitThreads / 32], wcnt[kFitThreads / 32];
+// point; fitness = sum d2 / count.  src0: ORIGINAL source (cell-sorted order).  Three kernels:
+//   icp_fitness_kernel        one thread per point, seeded by the last iteration's matches;
+//                             resolves every point whose search ball is a few cells wide and
+//                             queues the rest (points far off the target: ~4 % at the bench);
+//   icp_fitness_hard_kernel   one WARP per queued point (coarse-cell ring search), grid-stride
+//                             over the queue, so the expensive queries are spread over the
+//                             whole GPU instead of serialising the few warps that own them
+//                             (measured before the split: SMs active 29 % of the kernel);
+//   icp_fitness_reduce_kernel fixed-order sum of the per-point squared distances.
+// d2_all[i]: squared distance, -1 = no neighbour / not a finite point.
+struct FitQueue {
+  int* idx;         // queued point (position in src0)
+  int* seed;        // best candidate so far (sorted-target position) or -1
+  unsigned* count;  // queue length (reset by the reduce kernel)
+};
+
+__global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
+    icp_fitness_kernel(const IcpState* __restrict__ st, const __grid_constant__ GridDev g,
+                       const float4* __restrict__ src0, const int* __restrict__ Mj, int n,
+                       float* __restrict__ d2_all, const FitQueue fq, SearchStats* stats) {
   __shared__ float sT[16];
-  __shared__ double red[2];
   if (threadIdx.x < 16) sT[threadIdx.x] = st->Tfinal[threadIdx.x];
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = i < n;
   float4 q = active ? src0[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -602,24 +615,88 @@ __global__ void __launch_bounds__(kFitThreads)
   // seeded by the last iteration's matches (the final pose differs from the incremental one
   // only by float rounding), unbounded: every source point counts
   const int seed_j = (active && Mj) ? Mj[i] : -1;
-  Best b = nn_search_seeded(g, active, x, y, z, INFINITY, seed_j, stats);
-  const bool has = active && b.j >= 0;
-  double s = warp_sum(has ? (double)b.d2 : 0.0);
-  unsigned any = __ballot_sync(0xffffffffu, has);
-  if (lane == 0) {
-    wsum[w] = s;
-    wcnt[w] = (double)__popc(any);
+  bool deferred = false;
+  const Best b = nn_search_seeded<true>(g, active, x, y, z, INFINITY, seed_j, stats, &deferred);
+  const unsigned dm = __ballot_sync(0xffffffffu, deferred);
+  if (dm) {  // warp-aggregated append
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(fq.count, (unsigned)__popc(dm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (deferred) {
+      const unsigned pos = base + __popc(dm & ((1u << lane) - 1u));
+      fq.idx[pos] = i;
+      fq.seed[pos] = b.j;
+    }
   }
+  if (i < n) d2_all[i] = (active && !deferred && b.j >= 0) ? b.d2 : -1.0f;
+}
+
+__global__ void __launch_bounds__(128)
+    icp_fitness_hard_kernel(const IcpState* __restrict__ st, const __grid_constant__ GridDev g,
+                            const float4* __restrict__ src0, float* __restrict__ d2_all,
+                            const FitQueue fq) {
+  __shared__ float sT[16];
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->Tfinal[threadIdx.x];
   __syncthreads();
-  const int nblk = gridDim.x;
-  if (threadIdx.x < 2) {
-    double t = 0.0;
-    for (int ww = 0; ww < kFitThreads / 32; ++ww) t += threadIdx.x == 0 ? wsum[ww] : wcnt[ww];
-    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
+  const unsigned count = *fq.count;
+  const int lane = threadIdx.x & 31;
+  // contiguous queue chunks per warp: consecutive entries were appended together by one warp
+  // of the search kernel (Morton neighbours), so each result seeds the next query
+  const unsigned nw = gridDim.x * (blockDim.x >> 5);
+  const unsigned chunk = (count + nw - 1) / nw;
+  const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned p0 = w * chunk, p1 = min(count, p0 + chunk);
+  int last_j = -1;
+  for (unsigned pos = p0; pos < p1; ++pos) {
+    const int i = fq.idx[pos], sj = fq.seed[pos];
+    const float4 q = src0[i];
+    const float x = xform_row(sT, 0, q.x, q.y, q.z);
+    const float y = xform_row(sT, 1, q.x, q.y, q.z);
+    const float z = xform_row(sT, 2, q.x, q.y, q.z);
+    Best b;
+    b.d2 = INFINITY;
+    b.j = -1;
+    b.oi = 0x7fffffff;
+    if (sj >= 0) consider(__ldg(&g.pts[sj]), sj, x, y, z, b);
+    if (last_j >= 0) consider(__ldg(&g.pts[last_j]), last_j, x, y, z, b);
+    if (!nn_ball_warp(g, x, y, z, b)) nn_phase2_warp(g, x, y, z, b);
+    last_j = b.j;
+    if (lane == 0) d2_all[i] = b.j >= 0 ? b.d2 : -1.0f;
   }
+}
+
+constexpr int kFitReduceBlocks = 148;
+__global__ void __launch_bounds__(256)
+    icp_fitness_reduce_kernel(IcpState* __restrict__ st, const float* __restrict__ d2_all, int n,
+                              double* __restrict__ partials, unsigned* __restrict__ queue_count) {
+  __shared__ double ssum[256], scnt[256];
+  __shared__ double red[2];
   __shared__ unsigned s_ticket;
+  const int nblk = gridDim.x;
+  const int chunk = (n + nblk - 1) / nblk;
+  const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  double s = 0.0, c = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const float d2 = __ldcg(d2_all + i);
+    if (d2 >= 0.0f) {
+      s += (double)d2;
+      c += 1.0;
+    }
+  }
+  ssum[threadIdx.x] = s;
+  scnt[threadIdx.x] = c;
   __syncthreads();
+#pragma unroll
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+      scnt[threadIdx.x] += scnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
+    partials[blockIdx.x] = ssum[0];
+    partials[nblk + blockIdx.x] = scnt[0];
     __threadfence();
     s_ticket = atomicAdd(&st->ticket2, 1u);
   }
@@ -630,6 +707,7 @@ __global__ void __launch_bounds__(kFitThreads)
   __syncthreads();
   if (threadIdx.x == 0) {
     st->ticket2 = 0;
+    *queue_count = 0;
     st->fitness_sum = red[0];
     st->fitness_cnt = (long long)red[1];
   }

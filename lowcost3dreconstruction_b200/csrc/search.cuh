@@ -240,6 +240,61 @@ __device__ __forceinline__ int ball_halfwidth(const GridDev& g, float d2) {
   return w < 1.0e6f ? (int)ceilf(w) : 0x3fffffff;
 }
 
+// Warp-cooperative ball walk for ONE query (inputs and result uniform across the warp): the
+// (2W+1)^2 cell rows that can intersect the ball of the incoming candidate are dealt out to the
+// lanes 32 at a time, each lane scans the clipped run of its row, and the pruning bound is
+// refreshed (warp min) between steps.  For a query a few centimetres off the target this is a
+// handful of steps, where the super-cell ring search pays for whole 8^3 blocks.  Returns false
+// (nothing done) when there is no finite candidate or the window is too wide.
+constexpr int kCoopMaxW = 16;
+__device__ __forceinline__ bool nn_ball_warp(const GridDev& g, float qx, float qy, float qz, Best& b) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int W = ball_halfwidth(g, b.d2);
+  if (b.j < 0 || W > kCoopMaxW) return false;
+  const QueryCell qc = query_cell(g, qx, qy, qz);
+  const float inv_c2 = 1.0f / (g.c * g.c * 0.9999f);
+  const int side = 2 * W + 1, total = side * side;
+  const float inv_side = 1.0f / (float)side;
+  Best lb = b;
+  float bd = b.d2;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    if (t < total) {
+      const int rz = (int)(((float)t + 0.5f) * inv_side);  // exact: t < 33^2
+      const int dy = t - rz * side - W, dz = rz - W;
+      const int yy = qc.iy + dy, zz = qc.iz + dz;
+      if ((unsigned)yy < (unsigned)g.dy && (unsigned)zz < (unsigned)g.dz) {
+        const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
+        const float rem = bd * inv_c2 - (gy * gy + gz * gz);
+        if (rem >= 0.0f) {
+          const float wx = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
+          const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
+          if (xa <= xb) {
+            const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+            scan_run(g.pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, lb);
+          }
+        }
+      }
+    }
+    bd = fminf(bd, warp_min_f(lb.d2));
+  }
+  // lexicographic (d2, original index) min over the lanes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(full, lb.d2, o);
+    const int oj = __shfl_xor_sync(full, lb.j, o);
+    const int oo = __shfl_xor_sync(full, lb.oi, o);
+    if (od < lb.d2 || (od == lb.d2 && oo < lb.oi)) {
+      lb.d2 = od;
+      lb.j = oj;
+      lb.oi = oo;
+    }
+  }
+  b = lb;
+  return true;
+}
+
 // Walks the cell rows that intersect the lane's ball: rows culled by their y/z slab distance
 // against the shrinking bound, the x-run of each row clipped to the ball.  The row loops run
 // over the warp-wide window (lockstep); lanes mask themselves out of rows outside their ball.
@@ -285,8 +340,17 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
 // seed_j: position (sorted target order) of a plausible neighbour, e.g. the previous
 // iteration's match, or -1.  gate may be +inf (unbounded): lanes whose ball is too large for
 // the walk (or that found no candidate at all) go through the warp-cooperative ring search.
+// DEFER: lanes that the ball walk cannot resolve cheaply (window wider than kDeferW, or no
+// candidate at all) are NOT searched here: *deferred is set and the returned Best holds the
+// best candidate so far (a bound for whoever finishes the job).  A far query costs tens of
+// thousands of instructions; left to its own thread it serialises its whole warp and a
+// handful of such warps becomes the tail of the kernel — the caller queues these queries
+// for a warp-per-query pass spread over the whole GPU instead.
+constexpr int kDeferW = 2;
+template <bool DEFER = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, float qx, float qy,
-                                                 float qz, float gate, int seed_j, SearchStats* stats) {
+                                                 float qz, float gate, int seed_j, SearchStats* stats,
+                                                 bool* deferred = nullptr) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   Best b;
@@ -331,12 +395,13 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
   const bool borrowed = need && !seeded && !probed && b.j >= 0;
   // 4. ball walk for every lane whose ball is small enough, warp-cooperative rings otherwise
   const int Wl = need ? ball_halfwidth(g, b.d2) : 0;
-  const bool walk = need && Wl <= kBallMaxW;
+  const bool walk = need && Wl <= (DEFER ? kDeferW : kBallMaxW);
   unsigned n_cand = 0, n_rows = 0;
   if (__any_sync(full, walk))
     ball_walk(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
   if (walk) need = false;
-  unsigned todo = __ballot_sync(full, need);
+  if (DEFER) *deferred = need;
+  unsigned todo = DEFER ? 0u : __ballot_sync(full, need);
   if (stats) {
     unsigned mc = n_cand, mr = n_rows;
     for (int o = 16; o > 0; o >>= 1) {
@@ -346,13 +411,14 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
     const unsigned na = __popc(__ballot_sync(full, active && g.n > 0));
     const unsigned npb = __popc(__ballot_sync(full, probed)), nbr = __popc(__ballot_sync(full, borrowed));
     const unsigned nw = __popc(__ballot_sync(full, walk));
+    const unsigned n_left = __popc(__ballot_sync(full, need));  // ring searches / deferred
     if (lane == 0) {
       stat_add(stats, 0, na);
       stat_add(stats, 1, n_prev);
       stat_add(stats, 2, npb);
       stat_add(stats, 3, nbr);
       stat_add(stats, 4, nw);
-      stat_add(stats, 5, __popc(todo));
+      stat_add(stats, 5, n_left);
       stat_add(stats, 6, mc);
       stat_add(stats, 7, mr);
     }
