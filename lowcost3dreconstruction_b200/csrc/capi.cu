@@ -246,26 +246,29 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->pinned[1].ensure(sizeof(int) * (size_t)(p->max_iterations / kChunk + 2));
   int* h_done = ctx->pinned[1].as<int>();
   cudaEvent_t chunk_ev[2] = {ctx->chunk.a, ctx->chunk.b};
+  const bool pdl = !(std::getenv("LC3D_PDL") && std::atoi(std::getenv("LC3D_PDL")) == 0);
   auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
+    // programmatic dependent launch: each kernel of the chain is staged while its predecessor
+    // drains (the kernels call pdl_wait() before reading anything the predecessor wrote)
     if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
       if (want_stats)
-        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk, kIcpThreads, 0, d_state,
-                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       else
-        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, 0, d_state,
-                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
-      LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, 256, 0, d_state, cfg, partials,
-                  nwarps_icp, reduced);
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
+                      partials, nwarps_icp, reduced);
     } else {
       if (want_stats)
-        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk, kIcpThreads, 0, d_state,
-                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       else
-        LC3D_LAUNCH(ctx, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, 0, d_state,
-                    cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
-      LC3D_LAUNCH(ctx, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, 256, 0, d_state, cfg, partials,
-                  nwarps_icp, reduced);
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
+                      partials, nwarps_icp, reduced);
     }
   };
   {

@@ -172,6 +172,35 @@ struct lc3d_ctx {
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
 };
 
+namespace lc3d {
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled
+// before its predecessor in the stream has drained; it must call pdl_wait() before touching
+// anything the predecessor wrote.  pdl_trigger() lets the successor start launching early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(cudaStream_t stream, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace lc3d
+#define LC3D_LAUNCH_PDL(ctx, pdl, kernel, grid, block, ...)                                  \
+  do {                                                                                        \
+    LC3D_CUDA(lc3d::launch_pdl((ctx)->stream, (pdl), kernel, dim3(grid), dim3(block), __VA_ARGS__)); \
+    ++(ctx)->launches;                                                                        \
+  } while (0)
+
 #define LC3D_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
   do {                                                                        \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \

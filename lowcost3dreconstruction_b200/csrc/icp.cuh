@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
   __shared__ float sT[16];
   __shared__ int s_flags[2];
+  pdl_wait();  // the previous solve kernel's pose / done flag
   if (threadIdx.x == 0) {
     s_flags[0] = st->done;
     s_flags[1] = st->iter;
@@ -542,26 +543,40 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
 // Second kernel of an iteration: block v reduces estimator value v over all warp rows in a
 // fixed order (deterministic), the last block to finish (atomic ticket) solves, composes the
 // pose and runs the convergence test.  grid = NV blocks.
+constexpr int kSolveThreads = 512;
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSolveThreads)
     icp_solve_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const double* __restrict__ partials,
                      int nwarps, double* __restrict__ reduced) {
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
-  __shared__ double sm[256];
+  __shared__ double sm[kSolveThreads / 32];
   __shared__ unsigned s_ticket;
+  pdl_wait();     // the search kernel's partial rows
+  pdl_trigger();  // the next search kernel may stage its blocks behind this one
   if (st->done) return;
   const int v = blockIdx.x;
   const double* row = partials + (size_t)v * nwarps;
+  // fixed assignment and order (deterministic); 8 independent loads in flight per thread
   double s = 0.0;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < nwarps; i += 256) s += __ldcg(row + i);
-  sm[threadIdx.x] = s;
-  __syncthreads();
+  for (int base = threadIdx.x; base < nwarps; base += kSolveThreads * 8) {
+    double t[8];
 #pragma unroll
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-    __syncthreads();
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * kSolveThreads;
+      t[k] = i < nwarps ? __ldcg(row + i) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += t[k];
   }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < kSolveThreads / 32 ? sm[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sm[0] = t;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     reduced[v] = sm[0];
     __threadfence();
