@@ -22,9 +22,11 @@ thread_local std::string g_create_error;
 // scratch slots beyond the grid builder's
 enum {
   kScrRawA = kScrGridEnd, kScrRawB, kScrRawC, kScrRawD, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
-  kScrOutB, kScrDumpIdx, kScrDumpD2, kScrBound, kScrPrevMatch, kScrMisc, kScrMisc2, kScrMisc3, kScrEnd
+  kScrOutB, kScrDumpIdx, kScrDumpD2, kScrBound, kScrPrevMatch, kScrMisc, kScrMisc2, kScrMisc3,
+  kScrSrcSort0, kScrSrcSort1, kScrSrcSort2, kScrSrcSort3, kScrSrcSort4, kScrSrcSort5,  // private sort scratch
+  kScrEnd
 };
-static_assert(kScrEnd <= 32, "scratch slots");
+static_assert(kScrEnd <= 40, "scratch slots");
 
 struct Guard {  // sets the device for the duration of a call
   explicit Guard(lc3d_ctx* c) { LC3D_CUDA(cudaSetDevice(c->device)); }
@@ -161,8 +163,21 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // ---- spatial index over the target (KdTreeFLANN::setInputCloud) ----
   ctx->tm[1].start(st);
   Grid& G = *ctx->grid;
-  grid_build(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr,
-             tgt->n, cell_factor_env(), 0.0, xsub_env());
+  // plan (bbox, cell size: one host round trip), then the target fill (keys, sort, scan, gather)
+  // runs on the auxiliary stream while this stream orders the source along the Morton curve of
+  // the planned cells — two independent chains of short launch-bound kernels
+  grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env());
+  const bool two_streams = ctx->aux_stream != nullptr && !std::getenv("LC3D_NO_AUX");
+  {
+    struct StreamSwap {
+      lc3d_ctx* c;
+      cudaStream_t saved;
+      ~StreamSwap() { c->stream = saved; }
+    } swap{ctx, ctx->stream};
+    if (two_streams) ctx->stream = ctx->aux_stream;
+    grid_fill(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr, tgt->n);
+    if (two_streams) LC3D_CUDA(cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
+  }
   if (before_source) before_source();
   ctx->scratch[kScrSrcSorted].ensure((size_t)n * 16 + 16);
   ctx->scratch[kScrSrcWork].ensure((size_t)n * 16 + 16);
@@ -172,7 +187,8 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   float* Bnd = ctx->scratch[kScrBound].as<float>();
   ctx->scratch[kScrPrevMatch].ensure((size_t)n * 4 + 16);
   int* Mj = ctx->scratch[kScrPrevMatch].as<int>();
-  sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0, X);  // pristine + working copy
+  sort_queries_by_cell(ctx, G, src->xyz.as<float4>(), n, X0, X, kScrSrcSort0);  // pristine + working copy
+  if (two_streams) LC3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_aux, 0));
   ctx->tm[1].stop(st);
   // ---- the loop ----
   ctx->scratch[kScrState].ensure(sizeof(IcpState));
@@ -441,6 +457,8 @@ int lc3d_create(int device, void* stream, lc3d_ctx** out) {
     ctx->chunk.init();
     LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev_copy) LC3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    LC3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     ctx->grid = new Grid;
     *out = ctx;
     return LC3D_OK;
@@ -469,6 +487,8 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   for (auto& e : ctx->ev_copy)
     if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -239,8 +239,12 @@ enum { kScrBBox = 0, kScrProbe, kScrKeys, kScrVals, kScrKeysAlt, kScrValsAlt, kS
 
 // Builds the grid over `xyz` (n float4, input order).  cell_factor: cell edge in units of
 // the estimated point spacing.  min_cell > 0 forces a lower bound on the cell edge.
-inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
-                       double cell_factor, double min_cell = 0.0, int xsub = 1) {
+// Two phases so that callers can overlap independent work with the second one:
+//   grid_plan  bbox + density probe + ONE host round trip -> origin, cell edge, dims (everything
+//              a query needs to compute cell coordinates, e.g. the Morton order of the source);
+//   grid_fill  keys, sort, scan, gather (stream-ordered, no host sync).
+inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, double cell_factor,
+                      double min_cell = 0.0, int xsub = 1) {
   const int n = (int)n64;
   cudaStream_t st = ctx->stream;
   G.v = GridDev{};
@@ -345,6 +349,13 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   g.cdz = (g.dz + kCoarse - 1) >> kCoarseShift;
   g.n = nfinite;
   G.ncell = (int64_t)g.dx * g.dy * g.dz;
+}
+
+inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64) {
+  const int n = (int)n64;
+  if (n == 0) return;  // grid_plan set up the empty grid
+  cudaStream_t st = ctx->stream;
+  GridDev& g = G.v;
   const int64_t ncoarse = (int64_t)g.cdx * g.cdy * g.cdz;
   // 3. keys + histograms
   G.cell_start.ensure((size_t)(G.ncell + 2) * 4);
@@ -368,7 +379,9 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   // 4. stable radix sort of (cell id, point index)
   SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
                  ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
-  radix_sort_pairs(ctx, keys, vals, n, bit_length((uint32_t)G.ncell), ss);
+  uint32_t *skeys = nullptr, *svals = nullptr;
+  radix_sort_pairs(ctx, keys, vals, n, bit_length((uint32_t)G.ncell), ss, &skeys, &svals);
+  vals = svals;
   // 5. cell_start = exclusive scan of the cell histogram (ncell+1 entries)
   exclusive_scan_u32(ctx, cell_start, cell_start, G.ncell + 1, ctx->scratch[kScrScan].as<uint32_t>());
   // 6. gather into sorted SoA float4 (finite points come first: sentinel key sorts last)
@@ -378,6 +391,12 @@ inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* 
   g.coarse_cnt = G.coarse_cnt.as<uint32_t>();
   g.pts = G.pts.as<float4>();
   g.nrm = nrm ? G.nrm.as<float4>() : nullptr;
+}
+
+inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
+                       double cell_factor, double min_cell = 0.0, int xsub = 1) {
+  grid_plan(ctx, G, xyz, n64, cell_factor, min_cell, xsub);
+  grid_fill(ctx, G, xyz, nrm, n64);
 }
 
 // Orders `xyz` (n float4) along a Morton (Z-order) curve over the cells of grid g (clamped),
@@ -410,30 +429,35 @@ __global__ void __launch_bounds__(256)
   vals[i] = (uint32_t)i;
 }
 
+// Needs only grid_plan's result.  scr: first of 6 consecutive scratch slots (keys, vals, alt
+// keys, alt vals, histogram, scan) — pass a private range to run concurrently with grid_fill.
 inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz, int64_t n64,
-                                 float4* out_sorted, float4* out_sorted2 = nullptr) {
+                                 float4* out_sorted, float4* out_sorted2 = nullptr, int scr = kScrKeys) {
   const int n = (int)n64;
   if (n == 0) return;
-  ctx->scratch[kScrKeys].ensure((size_t)n * 4);
-  ctx->scratch[kScrVals].ensure((size_t)n * 4);
-  ctx->scratch[kScrKeysAlt].ensure((size_t)n * 4);
-  ctx->scratch[kScrValsAlt].ensure((size_t)n * 4);
-  ctx->scratch[kScrHist].ensure(sort_hist_bytes(n));
-  ctx->scratch[kScrScan].ensure(scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile)) + 64);
-  uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
-  uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
+  const int sKeys = scr, sVals = scr + 1, sKeysAlt = scr + 2, sValsAlt = scr + 3, sHist = scr + 4, sScan = scr + 5;
+  ctx->scratch[sKeys].ensure((size_t)n * 4);
+  ctx->scratch[sVals].ensure((size_t)n * 4);
+  ctx->scratch[sKeysAlt].ensure((size_t)n * 4);
+  ctx->scratch[sValsAlt].ensure((size_t)n * 4);
+  ctx->scratch[sHist].ensure(sort_hist_bytes(n));
+  ctx->scratch[sScan].ensure(scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile)) + 64);
+  uint32_t* keys = ctx->scratch[sKeys].as<uint32_t>();
+  uint32_t* vals = ctx->scratch[sVals].as<uint32_t>();
   int maxdim = std::max(G.v.dx >> G.v.xs_shift, std::max(G.v.dy, G.v.dz));
   int shift = 0;
   while ((maxdim >> shift) > 1024) ++shift;  // 10 bits per axis
   const int cb0 = bit_length((uint32_t)((maxdim - 1) >> shift));
   LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, (uint32_t)1u << (3 * cb0), keys, vals);
-  SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
-                 ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};
+  SortScratch ss{ctx->scratch[sKeysAlt].as<uint32_t>(), ctx->scratch[sValsAlt].as<uint32_t>(),
+                 ctx->scratch[sHist].as<uint32_t>(), ctx->scratch[sScan].as<uint32_t>()};
   // key bits actually used: 3 interleaved coordinates of bit_length((maxdim-1) >> shift) bits,
   // plus the non-finite sentinel bit 30 only if such points can exist (checked by the caller's
   // bbox count): sorting all 31 bits costs a fourth radix pass for nothing
   const int cb = bit_length((uint32_t)((maxdim - 1) >> shift));
-  radix_sort_pairs(ctx, keys, vals, n, std::min(31, 3 * cb + 1), ss);
+  uint32_t *skeys = nullptr, *svals = nullptr;
+  radix_sort_pairs(ctx, keys, vals, n, std::min(31, 3 * cb + 1), ss, &skeys, &svals);
+  vals = svals;
   LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, (const float4*)nullptr, vals, n,
               out_sorted, (float4*)nullptr, out_sorted2);
 }

@@ -150,6 +150,68 @@ __global__ void __launch_bounds__(kSmallScanThreads)
   }
 }
 
+// One-block exclusive scan for mid-sized inputs (the radix histograms of a pass: 256 x #tiles,
+// tens of thousands of entries): tiles of 4096 with coalesced 16-byte accesses and a running
+// carry, ONE launch instead of three launch-bound ones.
+constexpr int64_t kOneBlockScanMax = 65536;
+__global__ void __launch_bounds__(1024)
+    scan_one_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  __shared__ uint32_t wtot[32];
+  __shared__ uint32_t s_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < n; base += 4096) {
+    const int idx = base + threadIdx.x * 4;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    if (idx + 4 <= n) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + idx);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (idx + k < n) v[k] = in[idx + k];
+    }
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t t = wtot[lane];
+      uint32_t ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      wtot[lane] = ti - t;
+      if (lane == 31) s_total = ti;
+    }
+    __syncthreads();
+    uint32_t ex = carry + wtot[w] + inc - sum;
+    if (idx + 4 <= n) {
+      uint4 q;
+      q.x = ex; ex += v[0];
+      q.y = ex; ex += v[1];
+      q.z = ex; ex += v[2];
+      q.w = ex;
+      *reinterpret_cast<uint4*>(out + idx) = q;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (idx + k < n) out[idx + k] = ex;
+        ex += v[k];
+      }
+    }
+    carry += s_total;
+    __syncthreads();
+  }
+}
+
 // Exclusive scan of n uint32 (in may alias out).  `sums` scratch: >= div_up(n, kScanTile) u32.
 // Requires in/out 16-byte aligned (cudaMalloc'd).
 inline void exclusive_scan_u32(lc3d_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
@@ -157,6 +219,10 @@ inline void exclusive_scan_u32(lc3d_ctx* ctx, const uint32_t* in, uint32_t* out,
   if (n <= 0) return;
   if (n <= kSmallScanMax) {
     LC3D_LAUNCH(ctx, scan_small_kernel, 1, kSmallScanThreads, 0, in, out, (int)n);
+    return;
+  }
+  if (n <= kOneBlockScanMax) {
+    LC3D_LAUNCH(ctx, scan_one_block_kernel, 1, 1024, 0, in, out, (int)n);
     return;
   }
   int nb = div_up(n, kScanTile);
@@ -254,10 +320,15 @@ struct SortScratch {
 };
 inline size_t sort_hist_bytes(int64_t n) { return (size_t)kRadix * div_up(n, kSortTile) * 4 + 64; }
 
-// Sorts (keys, vals) ascending by the low `bits` bits of key, stable.  On return the
-// sorted data are in (keys, vals) (the function copies back if the pass count is odd).
+// Sorts (keys, vals) ascending by the low `bits` bits of key, stable.  The sorted data end up
+// in (keys, vals) or in the scratch pair, depending on the parity of the pass count: the
+// buffers holding the result are returned through out_keys / out_vals when given (no copy
+// back); otherwise the result is copied back into (keys, vals).
 inline void radix_sort_pairs(lc3d_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits,
-                             const SortScratch& s) {
+                             const SortScratch& s, uint32_t** out_keys = nullptr,
+                             uint32_t** out_vals = nullptr) {
+  if (out_keys) *out_keys = keys;
+  if (out_vals) *out_vals = vals;
   if (n <= 1) return;
   int passes = (bits + 7) / 8;
   if (passes < 1) passes = 1;
@@ -272,7 +343,10 @@ inline void radix_sort_pairs(lc3d_ctx* ctx, uint32_t* keys, uint32_t* vals, int6
     std::swap(kin, kout);
     std::swap(vin, vout);
   }
-  if (kin != keys) {
+  if (out_keys || out_vals) {
+    if (out_keys) *out_keys = kin;
+    if (out_vals) *out_vals = vin;
+  } else if (kin != keys) {
     LC3D_CUDA(cudaMemcpyAsync(keys, kin, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     LC3D_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   }
