@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(256)
   int iy = min(max((int)((q.y - oy) * sy), 0), kProbe - 1);
   int iz = min(max((int)((q.z - oz) * sz), 0), kProbe - 1);
   int c = (iz * kProbe + iy) * kProbe + ix;
-  uint32_t m = 1u << (c & 31);
-  if (!(bits[c >> 5] & m)) atomicOr(&bits[c >> 5], m);
+  // neighbouring points share probe cells: one atomic per distinct word per warp
+  const int word = c >> 5;
+  const uint32_t m = 1u << (c & 31);
+  const unsigned peers = __match_any_sync(__activemask(), word);
+  const uint32_t combined = __reduce_or_sync(peers, m);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1 && (bits[word] & combined) != combined) atomicOr(&bits[word], combined);
 }
 __global__ void __launch_bounds__(256) probe_count(const uint32_t* __restrict__ bits, int nwords,
                                                    uint32_t* out) {
@@ -200,11 +204,20 @@ __global__ void __launch_bounds__(256)
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
     int iz = min(max((int)floorf(cell_coord(q.z, g.oz, g.inv_c)), 0), g.dz - 1);
     key = (uint32_t)((iz * g.dy + iy) * g.dx + ix);
-    if (cell_cnt) atomicAdd(&cell_cnt[key], 1u);
-    if (coarse_cnt)
-      atomicAdd(&coarse_cnt[((iz >> kCoarseShift) * g.cdy + (iy >> kCoarseShift)) * g.cdx +
-                            (ix >> (kCoarseShift + g.xs_shift))],
-                1u);
+    // points arrive in scan order, so the lanes of a warp share a handful of cells: one
+    // atomic per distinct cell (and per distinct super-cell) per warp instead of one per point
+    const int lane = threadIdx.x & 31;
+    const unsigned act = __activemask();
+    if (cell_cnt) {
+      const unsigned peers = __match_any_sync(act, key);
+      if (lane == __ffs(peers) - 1) atomicAdd(&cell_cnt[key], (uint32_t)__popc(peers));
+    }
+    if (coarse_cnt) {
+      const uint32_t ck = (uint32_t)(((iz >> kCoarseShift) * g.cdy + (iy >> kCoarseShift)) * g.cdx +
+                                     (ix >> (kCoarseShift + g.xs_shift)));
+      const unsigned peers = __match_any_sync(act, ck);
+      if (lane == __ffs(peers) - 1) atomicAdd(&coarse_cnt[ck], (uint32_t)__popc(peers));
+    }
   }
   keys[i] = key;
   vals[i] = (uint32_t)i;

@@ -151,64 +151,73 @@ __global__ void __launch_bounds__(kSmallScanThreads)
 }
 
 // One-block exclusive scan for mid-sized inputs (the radix histograms of a pass: 256 x #tiles,
-// tens of thousands of entries): tiles of 4096 with coalesced 16-byte accesses and a running
-// carry, ONE launch instead of three launch-bound ones.
-constexpr int64_t kOneBlockScanMax = 65536;
+// tens of thousands of entries): ONE launch instead of three launch-bound ones.  Each thread
+// owns a contiguous chunk of up to 40 entries and issues all its loads up front (one memory
+// round trip), then one block scan of the thread totals.
+constexpr int kOneBlockVec = 10;                                  // uint4 per thread
+constexpr int64_t kOneBlockScanMax = 1024 * 4 * kOneBlockVec;     // 40960
 __global__ void __launch_bounds__(1024)
     scan_one_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
   __shared__ uint32_t wtot[32];
-  __shared__ uint32_t s_total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t carry = 0;
-  for (int base = 0; base < n; base += 4096) {
-    const int idx = base + threadIdx.x * 4;
-    uint32_t v[4] = {0u, 0u, 0u, 0u};
-    if (idx + 4 <= n) {
-      const uint4 q = *reinterpret_cast<const uint4*>(in + idx);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
+  // chunk length: multiple of 4 so that every chunk starts 16-byte aligned
+  const int per = (((n + 1023) >> 10) + 3) & ~3;
+  const int lo = threadIdx.x * per;
+  uint4 v[kOneBlockVec];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (idx + k < n) v[k] = in[idx + k];
+  for (int k = 0; k < kOneBlockVec; ++k) {
+    const int idx = lo + 4 * k;
+    v[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (4 * k < per) {
+      if (idx + 4 <= n) {
+        v[k] = *reinterpret_cast<const uint4*>(in + idx);
+      } else {
+        if (idx < n) v[k].x = in[idx];
+        if (idx + 1 < n) v[k].y = in[idx + 1];
+        if (idx + 2 < n) v[k].z = in[idx + 2];
+      }
     }
-    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
-    uint32_t inc = sum;
+  }
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kOneBlockVec; ++k) sum += v[k].x + v[k].y + v[k].z + v[k].w;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const uint32_t t = wtot[lane];
+    uint32_t ti = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
     }
-    if (lane == 31) wtot[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      const uint32_t t = wtot[lane];
-      uint32_t ti = t;
+    wtot[lane] = ti - t;
+  }
+  __syncthreads();
+  uint32_t ex = wtot[w] + inc - sum;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
-        if (lane >= o) ti += u;
-      }
-      wtot[lane] = ti - t;
-      if (lane == 31) s_total = ti;
-    }
-    __syncthreads();
-    uint32_t ex = carry + wtot[w] + inc - sum;
-    if (idx + 4 <= n) {
+  for (int k = 0; k < kOneBlockVec; ++k) {
+    const int idx = lo + 4 * k;
+    if (4 * k < per) {
       uint4 q;
-      q.x = ex; ex += v[0];
-      q.y = ex; ex += v[1];
-      q.z = ex; ex += v[2];
-      q.w = ex;
-      *reinterpret_cast<uint4*>(out + idx) = q;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (idx + k < n) out[idx + k] = ex;
-        ex += v[k];
+      q.x = ex; ex += v[k].x;
+      q.y = ex; ex += v[k].y;
+      q.z = ex; ex += v[k].z;
+      q.w = ex; ex += v[k].w;
+      if (idx + 4 <= n) {
+        *reinterpret_cast<uint4*>(out + idx) = q;
+      } else {
+        if (idx < n) out[idx] = q.x;
+        if (idx + 1 < n) out[idx + 1] = q.y;
+        if (idx + 2 < n) out[idx + 2] = q.z;
       }
     }
-    carry += s_total;
-    __syncthreads();
   }
 }
 
