@@ -39,6 +39,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=
 short = re.sub(r"\(.*", "", kname).split("::")[-1]
 short = re.sub(r"<.*", "", short).replace("void ", "").strip()
 targs = re.findall(r"<\(int\)(\d+)", kname)
+bargs = re.findall(r"\(bool\)(\d)", kname)
 cur_fn, line_of = None, {}
 cur_line = ("?", 0)
 for l in dis.splitlines():
@@ -49,6 +50,8 @@ for l in dis.splitlines():
     if cur_fn is None or short not in cur_fn:
         continue
     if targs and f"ILi{targs[0]}E" not in cur_fn and "ILi" in cur_fn:
+        continue
+    if bargs and f"Lb{bargs[0]}E" not in cur_fn and "Lb" in cur_fn:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
