@@ -193,6 +193,20 @@ int lc3d_sor(lc3d_ctx* ctx, const lc3d_cloud* cloud, int32_t mean_k, double stdd
 int lc3d_box_dedup(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* target, double radius,
                    int32_t* out_kept_index, int64_t* out_count);
 
+/* ------------------------------------------------------- cluster_extraction --- */
+
+/* Replaces pcl::EuclideanClusterExtraction::extract as pcl_tools/cluster_extraction.cpp:88-101
+ * drives it (setClusterTolerance / setMinClusterSize / setMaxClusterSize / extract; SURVEY 8f
+ * rank 4).  Clusters = connected components of the graph with an edge wherever the float32
+ * squared distance is < (float)(tolerance^2) (KdTreeFLANN::radiusSearch is strict), kept iff
+ * min_size <= size <= max_size, ranked by size descending (ties: the cluster holding the lower
+ * point index first — PCL leaves ties unspecified).  Non-finite points belong to no cluster.
+ * out_labels: caller-allocated cloud->n entries, rank of the point's cluster or -1;
+ * out_sizes (may be NULL): the first min(count, sizes_cap) cluster sizes by rank. */
+int lc3d_euclidean_clusters(lc3d_ctx* ctx, const lc3d_cloud* cloud, double tolerance, int64_t min_size,
+                            int64_t max_size, int32_t* out_labels, int64_t* out_sizes, int64_t sizes_cap,
+                            int64_t* out_count);
+
 /* ------------------------------------------------------------ transform ----- */
 
 /* pcl::transformPointCloudWithNormals (pcl_tools/transform.cpp:84-90; SURVEY §8f

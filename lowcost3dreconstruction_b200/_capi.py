@@ -81,7 +81,7 @@ SYMBOLS = [
     "lc3d_cloud_upload", "lc3d_cloud_free", "lc3d_dcloud_size",
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
-    "lc3d_voxel_grid", "lc3d_sor", "lc3d_transform", "lc3d_box_dedup",
+    "lc3d_voxel_grid", "lc3d_sor", "lc3d_transform", "lc3d_box_dedup", "lc3d_euclidean_clusters",
 ]
 
 
@@ -172,6 +172,8 @@ def _declare(lib):
     lib.lc3d_sor.restype = C.c_int
     lib.lc3d_box_dedup.argtypes = [vp, cp, cp, f64, vp, C.POINTER(i64)]
     lib.lc3d_box_dedup.restype = C.c_int
+    lib.lc3d_euclidean_clusters.argtypes = [vp, cp, f64, i64, i64, vp, vp, i64, C.POINTER(i64)]
+    lib.lc3d_euclidean_clusters.restype = C.c_int
     lib.lc3d_transform.argtypes = [vp, cp, C.POINTER(C.c_float), vp, vp]
     lib.lc3d_transform.restype = C.c_int
     return lib

@@ -243,6 +243,20 @@ def box_dedup(src, tgt, radius: float, ctx: Context | None = None) -> np.ndarray
     return kept[: cnt.value].copy()
 
 
+def euclidean_clusters(cloud, tolerance: float, min_size: int, max_size: int, ctx: Context | None = None):
+    """cluster_extraction.cpp:88-101 (pcl::EuclideanClusterExtraction::extract): returns
+    (labels, sizes) — labels[i] = rank of point i's cluster (size descending) or -1."""
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    labels = np.empty(max(c.n, 1), dtype=np.int32)
+    sizes = np.zeros(max(c.n, 1), dtype=np.int64)
+    cnt = C.c_int64(0)
+    ctx._check(ctx._lib.lc3d_euclidean_clusters(ctx._h, c.ref(), float(tolerance), int(min_size), int(max_size),
+                                                labels.ctypes.data, sizes.ctypes.data, sizes.size,
+                                                C.byref(cnt)), "lc3d_euclidean_clusters")
+    return labels[: c.n].copy(), sizes[: cnt.value].copy()
+
+
 def transform(cloud, T, ctx: Context | None = None):
     ctx = ctx or default_context()
     c = _hc(cloud)
@@ -346,6 +360,35 @@ class VoxelGrid:
 
     def filter(self):
         return voxel_grid(self._cloud, self._leaf, ctx=self._ctx)
+
+
+class EuclideanClusterExtraction:
+    """pcl::EuclideanClusterExtraction as used at cluster_extraction.cpp:94-101."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx, self._cloud, self._tol, self._min, self._max = ctx, None, 0.0, 1, 2 ** 31 - 1
+
+    def setInputCloud(self, cloud):
+        self._cloud = _hc(cloud)
+
+    def setClusterTolerance(self, t):
+        self._tol = float(t)
+
+    def setMinClusterSize(self, n):
+        self._min = int(n)
+
+    def setMaxClusterSize(self, n):
+        self._max = int(n)
+
+    def setSearchMethod(self, tree=None):  # the grid index replaces the kd-tree
+        pass
+
+    def extract(self):
+        """List of index arrays (ascending indices), largest cluster first."""
+        labels, sizes = euclidean_clusters(self._cloud, self._tol, self._min, self._max, ctx=self._ctx)
+        order = np.argsort(labels, kind="stable")
+        order = order[labels[order] >= 0]
+        return np.split(order.astype(np.int32), np.cumsum(sizes)[:-1]) if len(sizes) else []
 
 
 class StatisticalOutlierRemoval:

@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "dedup.cuh"
+#include "cluster.cuh"
 #include "grid.cuh"
 #include "icp.cuh"
 #include "knn.cuh"

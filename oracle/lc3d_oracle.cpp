@@ -144,7 +144,52 @@ struct KdTree {
     return r.count;
   }
 
+  // Radius search as FLANN's RadiusResultSet does it (KdTreeFLANN::radiusSearch):
+  // every indexed point with d2 < r2 STRICTLY, r2 = (float)(radius * radius); unordered.
+  void radius(const float* q, float r2, std::vector<int32_t>& out) const {
+    out.clear();
+    if (n == 0) return;
+    double dists[3] = {0, 0, 0};
+    double mind = 0;
+    for (int d = 0; d < 3; ++d) {
+      if (q[d] < bb_lo[d]) dists[d] = sq((double)q[d] - (double)bb_lo[d]);
+      if (q[d] > bb_hi[d]) dists[d] = sq((double)q[d] - (double)bb_hi[d]);
+      mind += dists[d];
+    }
+    search_radius(0, q, mind, dists, r2, out);
+  }
+
  private:
+  void search_radius(int32_t ni, const float* q, double mind, double* dists, float r2,
+                     std::vector<int32_t>& out) const {
+    const Node& nd = nodes[ni];
+    if (nd.divfeat < 0) {
+      for (int32_t i = nd.left; i < nd.right; ++i)
+        if (dist2(q, &pts[i].x) < r2) out.push_back(order[i]);
+      return;
+    }
+    int f = nd.divfeat;
+    double v = q[f];
+    double d1 = v - (double)nd.divlow, d2 = v - (double)nd.divhigh;
+    int32_t best, other;
+    double cutd;
+    if (d1 + d2 < 0) {
+      best = nd.child1;
+      other = nd.child2;
+      cutd = sq(v - (double)nd.divhigh);
+    } else {
+      best = nd.child2;
+      other = nd.child1;
+      cutd = sq(v - (double)nd.divlow);
+    }
+    search_radius(best, q, mind, dists, r2, out);
+    double save = dists[f];
+    double m2 = mind + cutd - save;
+    dists[f] = cutd;
+    if (m2 * (1.0 - 1e-6) <= (double)r2) search_radius(other, q, m2, dists, r2, out);
+    dists[f] = save;
+  }
+
   const P3* src_ = nullptr;
   std::vector<int32_t> idx_;
 
@@ -1193,6 +1238,55 @@ int orc_box_dedup(const lc3d_cloud* src, const lc3d_cloud* tgt, double radius, i
   for (int64_t i = 0; i < src->n; ++i)
     if (alive[i]) out_kept[c++] = (int32_t)i;
   *out_count = c;
+  return 0;
+}
+
+// pcl::EuclideanClusterExtraction::extract (pcl_tools/cluster_extraction.cpp:94-101; PCL 1.8.1
+// segmentation/impl/extract_clusters.hpp extractEuclideanClusters): breadth-first growth from
+// every unprocessed point over radiusSearch(point, tolerance) neighbours, a queue is kept as a
+// cluster iff min_size <= size <= max_size, each cluster's indices sorted ascending, clusters
+// sorted by size descending (std::sort on reverse iterators: ties unspecified in PCL — here
+// ties go to the cluster holding the lower point index).  Non-finite points are never part
+// of a cluster (PCL asserts on them).  labels[i] = rank of the cluster of point i, or -1.
+// sizes[0..min(count,cap)) = cluster sizes by rank.
+int orc_euclidean_clusters(const lc3d_cloud* cloud, double tolerance, int64_t min_size, int64_t max_size,
+                           int32_t* labels, int64_t* sizes, int64_t cap, int64_t* out_count) {
+  const int64_t n = cloud->n;
+  KdTree tree;
+  tree.build(cloud);
+  const float r2 = (float)(tolerance * tolerance);
+  std::vector<char> processed(n, 0);
+  std::vector<std::vector<int32_t>> clusters;
+  std::vector<int32_t> nn, queue;
+  for (int64_t i = 0; i < n; ++i) labels[i] = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    if (processed[i]) continue;
+    processed[i] = 1;
+    if (!finite3(xyz_at(cloud, i))) continue;
+    queue.clear();
+    queue.push_back((int32_t)i);
+    for (size_t h = 0; h < queue.size(); ++h) {
+      tree.radius(xyz_at(cloud, queue[h]), r2, nn);
+      for (int32_t j : nn) {
+        if (processed[j]) continue;
+        processed[j] = 1;
+        queue.push_back(j);
+      }
+    }
+    if ((int64_t)queue.size() >= min_size && (int64_t)queue.size() <= max_size) {
+      std::sort(queue.begin(), queue.end());
+      clusters.push_back(queue);
+    }
+  }
+  std::sort(clusters.begin(), clusters.end(), [](const std::vector<int32_t>& a, const std::vector<int32_t>& b) {
+    if (a.size() != b.size()) return a.size() > b.size();
+    return a[0] < b[0];
+  });
+  for (size_t c = 0; c < clusters.size(); ++c) {
+    for (int32_t j : clusters[c]) labels[j] = (int32_t)c;
+    if ((int64_t)c < cap && sizes) sizes[c] = (int64_t)clusters[c].size();
+  }
+  *out_count = (int64_t)clusters.size();
   return 0;
 }
 

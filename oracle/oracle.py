@@ -57,6 +57,8 @@ def load():
     lib.orc_voxel_grid.restype = C.c_int
     lib.orc_box_dedup.argtypes = [cp, cp, f64, vp, C.POINTER(i64)]
     lib.orc_box_dedup.restype = C.c_int
+    lib.orc_euclidean_clusters.argtypes = [cp, f64, i64, i64, vp, vp, i64, C.POINTER(i64)]
+    lib.orc_euclidean_clusters.restype = C.c_int
     lib.orc_transform.argtypes = [cp, C.POINTER(C.c_float), vp, vp]
     lib.orc_transform.restype = None
     lib.orc_kabsch_rotation.argtypes = [C.POINTER(f64), C.POINTER(f64)]
@@ -189,6 +191,16 @@ def box_dedup(src, tgt, radius: float):
     cnt = C.c_int64(0)
     load().orc_box_dedup(s.ref(), t.ref(), float(radius), kept.ctypes.data, C.byref(cnt))
     return kept[: cnt.value].copy()
+
+
+def euclidean_clusters(cloud, tolerance: float, min_size: int, max_size: int):
+    c = _hc(cloud)
+    labels = np.empty(max(c.n, 1), dtype=np.int32)
+    sizes = np.zeros(max(c.n, 1), dtype=np.int64)
+    cnt = C.c_int64(0)
+    load().orc_euclidean_clusters(c.ref(), float(tolerance), int(min_size), int(max_size), labels.ctypes.data,
+                                  sizes.ctypes.data, sizes.size, C.byref(cnt))
+    return labels[: c.n].copy(), sizes[: cnt.value].copy()
 
 
 def transform(cloud, T):

@@ -218,3 +218,41 @@ def test_accumulate_clouds_dedup(ply_pair, ctx):
     assert np.array_equal(pts["xyz"][: len(tgt)], tgt) and np.array_equal(pts["xyz"][len(tgt):], want)
     assert np.array_equal(plyutil.read_pcl_binary(str(d / "acc_dedup_negative.ply"))["xyz"], want)
     assert "|----|----|" in out  # the progress banner the reference prints on stdout
+
+
+def test_cluster_extraction_cli_contract(tmp_path):
+    rc, out, _ = run("cluster_extraction", "--help")
+    assert rc == 0 and out.startswith("Euclidean cluster extraction.")
+    for o in ("-f [ --outliers_file ]", "-p [ --cluster_percentage ] arg (=0.25)",
+              "-t [ --tolerance ] arg (=0.02)"):
+        assert o in out
+    rc, _, err = run("cluster_extraction")
+    assert rc == 255 and err.startswith("Correct mode of use: ") and err.strip().endswith("-i input.ply -o output.ply")
+    rc, _, err = run("cluster_extraction", "-i", "a", "-o", "b", "-p", "1.5")
+    assert rc == 255 and err.strip() == "cluster_percentage must be a value between 0 and 1"
+    rc, _, err = run("cluster_extraction", "-i", "/nonexistent.ply", "-o", str(tmp_path / "o.ply"))
+    assert rc == 255 and err.strip() == "Couldn't load input point cloud: /nonexistent.ply"
+
+
+@pytest.mark.gpu
+def test_cluster_extraction_matches_oracle(tmp_path):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    a = (rng.normal(size=(4000, 3)) * 0.03).astype(np.float32)
+    b = (rng.normal(size=(2500, 3)) * 0.03).astype(np.float32) + np.array([0.6, 0, 0], np.float32)
+    c = rng.uniform(-1, 1, size=(300, 3)).astype(np.float32)
+    pts = np.round(np.concatenate([a, b, c]).astype(np.float64), 6)
+    pts = pts[rng.permutation(len(pts))]
+    i, o = str(tmp_path / "in.ply"), str(tmp_path / "out.ply")
+    plyutil.write_capture_ascii(i, pts)
+    x = pts.astype(np.float32)
+    rc, out, err = run("cluster_extraction", "-i", i, "-o", o, "-t", "0.02", "-p", "0.2", "-f")
+    assert rc == 0, err
+    labels, sizes = orc.euclidean_clusters(x, 0.02, int(len(x) * 0.2), len(x))
+    assert len(sizes) == 2 and f"{len(sizes)} cluster(s) extracted." in out
+    want = np.concatenate([np.flatnonzero(labels == r) for r in range(len(sizes))])
+    assert np.array_equal(plyutil.read_pcl_binary(o)["xyz"], x[want])
+    assert np.array_equal(plyutil.read_pcl_binary(str(tmp_path / "out_outliers.ply"))["xyz"], x[labels < 0])
+    # nothing large enough: the reference's error path
+    rc, out, err = run("cluster_extraction", "-i", i, "-o", o, "-t", "0.0001", "-p", "0.9")
+    assert rc == 255 and err.strip() == "Could not extact clusters for the given dataset"

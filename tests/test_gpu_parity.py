@@ -368,3 +368,40 @@ def test_box_dedup_bit_exact(ctx, pair, radius):
     assert np.array_equal(api.box_dedup(s, t, radius, ctx=ctx), orc.box_dedup(s, t, radius))
     assert len(api.box_dedup(s, np.zeros((0, 3), np.float32), radius, ctx=ctx)) == len(s) - 1   # only the NaN goes
     assert len(api.box_dedup(tgt, tgt, radius, ctx=ctx)) == 0                                    # everything is redundant
+
+
+@pytest.mark.parametrize("tol,lo", [(0.004, 30), (0.02, 100), (0.0015, 1)])
+def test_euclidean_clusters_bit_exact(ctx, pair, tol, lo):
+    """cluster_extraction.cpp:94-101: per-point cluster ranks identical to the BFS restatement."""
+    src, tgt = pair
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([tgt[rng.choice(len(tgt), 15000, replace=False)],
+                          rng.uniform(-0.6, 0.6, (300, 3)).astype(np.float32) + np.array([0, 0, 0.9], np.float32)])
+    pts[123] = np.nan
+    g_lab, g_sz = api.euclidean_clusters(pts, tol, lo, len(pts), ctx=ctx)
+    o_lab, o_sz = orc.euclidean_clusters(pts, tol, lo, len(pts))
+    assert np.array_equal(g_sz, o_sz) and np.array_equal(g_lab, o_lab)
+    assert g_lab[123] == -1
+    # PCL-named wrapper: index lists, largest cluster first, indices ascending
+    ec = api.EuclideanClusterExtraction(ctx)
+    ec.setInputCloud(pts)
+    ec.setClusterTolerance(tol)
+    ec.setMinClusterSize(lo)
+    ec.setMaxClusterSize(len(pts))
+    cl = ec.extract()
+    assert [len(c) for c in cl] == o_sz.tolist()
+    for r, c in enumerate(cl):
+        assert np.array_equal(c, np.flatnonzero(o_lab == r))
+
+
+def test_euclidean_clusters_edge_cases(ctx):
+    e = np.zeros((0, 3), np.float32)
+    assert api.euclidean_clusters(e, 0.1, 1, 10, ctx=ctx)[1].tolist() == []
+    two = np.array([[0, 0, 0], [0.5, 0, 0]], np.float32)
+    assert api.euclidean_clusters(two, 0.5, 1, 2, ctx=ctx)[1].tolist() == [1, 1]        # strict radius
+    assert api.euclidean_clusters(two, 0.5000001, 1, 2, ctx=ctx)[1].tolist() == [2]
+    lab, sz = api.euclidean_clusters(two, 0.6, 3, 10, ctx=ctx)                            # too small: no cluster
+    assert sz.tolist() == [] and lab.tolist() == [-1, -1]
+    same = np.zeros((100, 3), np.float32)                                                # duplicates
+    lab, sz = api.euclidean_clusters(same, 1e-3, 1, 100, ctx=ctx)
+    assert sz.tolist() == [100] and (lab == 0).all()

@@ -238,3 +238,39 @@ def test_box_dedup_against_numpy():
         inside = ((src[:, None, :] >= lo[None]) & (src[:, None, :] <= hi[None])).all(-1).any(-1)
         want = np.flatnonzero(~inside & np.isfinite(src).all(1))
         assert np.array_equal(kept, want)
+
+
+def test_euclidean_clusters_against_connected_components():
+    """extractEuclideanClusters == connected components of the strict d2 < (float)(tol^2) graph,
+    filtered by size, ranked by size descending (ties: lower first index)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(7)
+    a = (rng.normal(size=(900, 3)) * 0.05).astype(np.float32)
+    b = (rng.normal(size=(600, 3)) * 0.05).astype(np.float32) + np.array([1, 0, 0], np.float32)
+    c = rng.uniform(-3, 3, size=(150, 3)).astype(np.float32)
+    pts = np.concatenate([a, b, c])
+    rng.shuffle(pts)
+    pts[17] = np.nan
+    tol = 0.05
+    for lo, hi in ((50, len(pts)), (1, len(pts)), (2, 700)):
+        labels, sizes = orc.euclidean_clusters(pts, tol, lo, hi)
+        fin = np.isfinite(pts).all(1)
+        d = (pts[:, None, :] - pts[None, :, :]).astype(np.float32) ** 2
+        d2 = (d[:, :, 0] + d[:, :, 1]) + d[:, :, 2]
+        adj = (d2 < np.float32(tol * tol)) & fin[:, None] & fin[None, :]
+        nc, comp = connected_components(coo_matrix(adj), directed=False)
+        cnt = np.bincount(comp, minlength=nc)
+        first = np.full(nc, len(pts))
+        np.minimum.at(first, comp, np.arange(len(pts)))
+        keep = [k for k in range(nc) if lo <= cnt[k] <= hi and fin[first[k]]]
+        keep.sort(key=lambda k: (-cnt[k], first[k]))
+        want = np.full(len(pts), -1, np.int32)
+        for r, k in enumerate(keep):
+            want[comp == k] = r
+        assert np.array_equal(labels, want)
+        assert np.array_equal(sizes, [cnt[k] for k in keep])
+    # the radius test is strict: two points exactly `tol` apart are NOT neighbours
+    two = np.array([[0, 0, 0], [0.5, 0, 0]], np.float32)
+    assert orc.euclidean_clusters(two, 0.5, 1, 2)[1].tolist() == [1, 1]
+    assert orc.euclidean_clusters(two, 0.5000001, 1, 2)[1].tolist() == [2]
