@@ -346,7 +346,10 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
 // thousands of instructions; left to its own thread it serialises its whole warp and a
 // handful of such warps becomes the tail of the kernel — the caller queues these queries
 // for a warp-per-query pass spread over the whole GPU instead.
-constexpr int kDeferW = 2;
+#ifndef LC3D_DEFER_W
+#define LC3D_DEFER_W 2
+#endif
+constexpr int kDeferW = LC3D_DEFER_W;
 template <bool DEFER = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, float qx, float qy,
                                                  float qz, float gate, int seed_j, SearchStats* stats,
