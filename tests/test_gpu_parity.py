@@ -101,6 +101,39 @@ def test_nn_volumetric_random(ctx):
         assert np.array_equal(gi, oi) and np.array_equal(gd, od)
 
 
+def test_nn_anisotropic_grid_shapes(ctx):
+    """The index slices its cells 8x along x (GridDev::xs) and backs off when x is the long axis:
+    exercise the subdivision limits with clouds stretched along each axis."""
+    rng = np.random.default_rng(21)
+    for axis, length in ((0, 100.0), (1, 100.0), (2, 100.0), (0, 0.0)):
+        tgt = rng.normal(0, 0.01, (12000, 3)).astype(np.float32)
+        tgt[:, axis] = rng.uniform(0, length, len(tgt)).astype(np.float32) if length else np.float32(0.5)
+        q = tgt[rng.choice(len(tgt), 6000)] + rng.normal(0, 0.02, (6000, 3)).astype(np.float32)
+        for md in (0.0, 0.03):
+            oi, od = orc.KdTree(tgt).nn(q, md)
+            gi, gd = api.nn(tgt, q, md, ctx=ctx)
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        s = q[:4000]
+        o = orc.icp_align(s, tgt, 0.05, 8, dump_iteration=2)
+        g = api.icp_align(s, tgt, 0.05, 8, dump_iteration=2, ctx=ctx)
+        assert g["iterations"] == o["iterations"] and np.array_equal(g["corr_index"], o["corr_index"])
+
+
+def test_nn_large_cloud_sort_paths(ctx):
+    """> 327k points: the radix histograms outgrow the one-block scan (3-kernel scan path)."""
+    rng = np.random.default_rng(22)
+    tgt = rng.uniform(-1, 1, (420000, 3)).astype(np.float32)
+    tgt[:, 2] = np.float32(0.3) * np.sin(3 * tgt[:, 0]) * np.cos(2 * tgt[:, 1])   # a surface, like a scan
+    q = tgt[rng.choice(len(tgt), 50000)] + rng.normal(0, 0.004, (50000, 3)).astype(np.float32)
+    oi, od = orc.KdTree(tgt).nn(q, 0.02)
+    gi, gd = api.nn(tgt, q, 0.02, ctx=ctx)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    # percolation threshold of this sampling: 1225 clusters of 50..5666 points, many size ties
+    lab, sz = api.euclidean_clusters(tgt[:350000], 0.004, 50, 350000, ctx=ctx)
+    ol, osz = orc.euclidean_clusters(tgt[:350000], 0.004, 50, 350000)
+    assert len(osz) > 1000 and np.array_equal(sz, osz) and np.array_equal(lab, ol)
+
+
 # ------------------------------------------------------------------------------- ICP
 
 @pytest.mark.parametrize("dump_it", [0, 4, 12])
