@@ -68,10 +68,13 @@ struct PendingUpload {
   const unsigned char* raw_xyz = nullptr;
   const unsigned char* raw_nrm = nullptr;
   cudaEvent_t ready = nullptr;  // recorded on the copy stream after the last byte, or null
+  // normals staged separately (upload_begin_normals) so that other arrays can go first
+  bool normals_deferred = false;
+  cudaEvent_t ready_nrm = nullptr;
 };
 
 PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals, DevBuf& raw_a,
-                           DevBuf& raw_b, cudaStream_t cs, cudaEvent_t ready) {
+                           DevBuf& raw_b, cudaStream_t cs, cudaEvent_t ready, bool defer_normals = false) {
   PendingUpload pu;
   pu.h = h;
   pu.d = d;
@@ -91,13 +94,36 @@ PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, b
   const bool same_block = want_normals && h->normal && h->normal_stride == h->xyz_stride && off >= 0 &&
                           off + 12 <= h->xyz_stride;
   pu.raw_xyz = stage_raw(ctx, raw_a, h->xyz, h->xyz_stride, n, same_block ? (int)off + 12 : 12, cs);
-  if (want_normals && h->normal)
-    pu.raw_nrm = same_block ? pu.raw_xyz + off : stage_raw(ctx, raw_b, h->normal, h->normal_stride, n, 12, cs);
+  if (want_normals && h->normal) {
+    if (same_block)
+      pu.raw_nrm = pu.raw_xyz + off;
+    else if (defer_normals)
+      pu.normals_deferred = true;  // staged by upload_begin_normals
+    else
+      pu.raw_nrm = stage_raw(ctx, raw_b, h->normal, h->normal_stride, n, 12, cs);
+    d->has_normal = true;  // contents arrive with upload_finish / upload_finish_normals
+  }
   if (ready) {
     LC3D_CUDA(cudaEventRecord(ready, cs ? cs : ctx->stream));
     pu.ready = ready;
   }
   return pu;
+}
+
+// Second half of a split upload: the normals follow on the copy stream (after whatever the
+// caller queued in between) with their own completion event.
+void upload_begin_normals(lc3d_ctx* ctx, PendingUpload& pu, DevBuf& raw_b, cudaStream_t cs, cudaEvent_t ready) {
+  if (!pu.normals_deferred || pu.h->n == 0) return;
+  pu.raw_nrm = stage_raw(ctx, raw_b, pu.h->normal, pu.h->normal_stride, pu.h->n, 12, cs);
+  LC3D_CUDA(cudaEventRecord(ready, cs ? cs : ctx->stream));
+  pu.ready_nrm = ready;
+}
+// Unpacks deferred normals on the CURRENT compute stream of the context once they have landed.
+void upload_finish_normals(lc3d_ctx* ctx, const PendingUpload& pu) {
+  if (!pu.normals_deferred || pu.h->n == 0) return;
+  LC3D_CUDA(cudaStreamWaitEvent(ctx->stream, pu.ready_nrm, 0));
+  LC3D_LAUNCH(ctx, unpack_strided, div_up(pu.h->n, 256), 256, 0, pu.raw_nrm, pu.h->normal_stride, (int)pu.h->n,
+              0.0f, (const unsigned char*)nullptr, (int64_t)0, pu.d->normal.as<float4>());
 }
 
 void upload_finish(lc3d_ctx* ctx, const PendingUpload& pu) {
@@ -106,7 +132,7 @@ void upload_finish(lc3d_ctx* ctx, const PendingUpload& pu) {
   if (pu.ready) LC3D_CUDA(cudaStreamWaitEvent(ctx->stream, pu.ready, 0));
   LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_xyz, pu.h->xyz_stride, (int)n, 1.0f,
               (const unsigned char*)nullptr, (int64_t)0, pu.d->xyz.as<float4>());
-  if (pu.raw_nrm) {
+  if (pu.raw_nrm && !pu.normals_deferred) {
     LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_nrm, pu.h->normal_stride, (int)n, 0.0f,
                 (const unsigned char*)nullptr, (int64_t)0, pu.d->normal.as<float4>());
     pu.d->has_normal = true;
@@ -151,9 +177,17 @@ double knn_cell_factor_env() {
 // (the host-buffer path finishes the source upload there, so that copy overlaps the build).
 // overlap_download: move the registered cloud to the host on the copy stream while
 // getFitnessScore runs.
+// Hooks of the host-buffer path, each called stream-ordered right before the data is first read:
+// the uploads still in flight are finished as late as possible.
+struct IcpHooks {
+  std::function<void()> before_source;          // source xyz (first read by the Morton ordering)
+  std::function<void()> before_target_normals;  // target normals (first read by the index gather)
+  std::function<void()> before_source_normals;  // source normals (first read by the registered-cloud transform)
+};
 void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, const lc3d_icp_params* p,
-             lc3d_icp_result* res, const lc3d_icp_outputs* out,
-             const std::function<void()>& before_source = nullptr, bool overlap_download = false) {
+             lc3d_icp_result* res, const lc3d_icp_outputs* out, const IcpHooks& hooks = IcpHooks(),
+             bool overlap_download = false) {
+  const std::function<void()>& before_source = hooks.before_source;
   cudaStream_t st = ctx->stream;
   const int n = (int)src->n;
   if (p->max_iterations <= 0) throw CudaError{"max_iterations needs to be greater than zero."};
@@ -176,7 +210,8 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
       ~StreamSwap() { c->stream = saved; }
     } swap{ctx, ctx->stream};
     if (two_streams) ctx->stream = ctx->aux_stream;
-    grid_fill(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr, tgt->n);
+    grid_fill(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr, tgt->n,
+              hooks.before_target_normals);
     if (two_streams) LC3D_CUDA(cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
   }
   if (before_source) before_source();
@@ -320,6 +355,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     ctx->scratch[kScrOutA].ensure((size_t)n * 12);
     const bool wn = out->registered_normal && src->has_normal;
     if (wn) ctx->scratch[kScrOutB].ensure((size_t)n * 12);
+    if (wn && hooks.before_source_normals) hooks.before_source_normals();
     LC3D_LAUNCH(ctx, transform_kernel, div_up(n, 256), 256, 0, d_state->Tfinal,
                 src->xyz.as<float4>(), wn ? src->normal.as<float4>() : nullptr, n,
                 ctx->scratch[kScrOutA].as<float>(), wn ? ctx->scratch[kScrOutB].as<float>() : nullptr);
@@ -465,6 +501,7 @@ int lc3d_create(int device, void* stream, lc3d_ctx** out) {
     ctx->chunk.init();
     LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev_copy) LC3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ctx->ev_up) LC3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     LC3D_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     LC3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     ctx->grid = new Grid;
@@ -496,6 +533,8 @@ void lc3d_destroy(lc3d_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+  for (auto& e : ctx->ev_up)
+    if (e) cudaEventDestroy(e);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -555,16 +594,30 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
     ctx->tm[5].start(ctx->stream);
     ctx->tm[0].start(ctx->stream);
     const bool need_src_normals = outputs && outputs->registered_normal;
-    // all four host->device copies go out on the copy stream right away; the compute stream
-    // waits for the target only, builds the index while the source is still in flight
+    // All four host->device copies go out on the copy stream right away, in the order the
+    // device needs them: target xyz (bbox, cell size), source xyz (Morton ordering, concurrent
+    // with the target fill), target normals (first read by the index gather), source normals
+    // (first read after the loop).  Each array is unpacked, stream-ordered, right before its
+    // first use.
     cudaStream_t cs = ctx->copy_stream;
-    const PendingUpload pt = upload_begin(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE,
-                                          ctx->scratch[kScrRawA], ctx->scratch[kScrRawB], cs, ctx->ev_copy[0]);
-    const PendingUpload ps = upload_begin(ctx, source, &tc.a, need_src_normals, ctx->scratch[kScrRawC],
-                                          ctx->scratch[kScrRawD], cs, ctx->ev_copy[1]);
-    upload_finish(ctx, pt);
-    ctx->tm[0].stop(ctx->stream);
-    icp_run(ctx, &tc.a, &tc.b, params, result, outputs, [&] { upload_finish(ctx, ps); }, true);
+    try {
+      PendingUpload pt = upload_begin(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE,
+                                      ctx->scratch[kScrRawA], ctx->scratch[kScrRawB], cs, ctx->ev_up[0], true);
+      PendingUpload ps = upload_begin(ctx, source, &tc.a, need_src_normals, ctx->scratch[kScrRawC],
+                                      ctx->scratch[kScrRawD], cs, ctx->ev_up[1], true);
+      upload_begin_normals(ctx, pt, ctx->scratch[kScrRawB], cs, ctx->ev_up[2]);
+      upload_begin_normals(ctx, ps, ctx->scratch[kScrRawD], cs, ctx->ev_up[3]);
+      upload_finish(ctx, pt);
+      ctx->tm[0].stop(ctx->stream);
+      IcpHooks hooks;
+      hooks.before_source = [&] { upload_finish(ctx, ps); };
+      hooks.before_target_normals = [&] { upload_finish_normals(ctx, pt); };
+      hooks.before_source_normals = [&] { upload_finish_normals(ctx, ps); };
+      icp_run(ctx, &tc.a, &tc.b, params, result, outputs, hooks, true);
+    } catch (...) {
+      if (cs) cudaStreamSynchronize(cs);  // no copy may still read the caller's buffers
+      throw;
+    }
     result->ms_upload = ctx->tm[0].ms();
   });
 }

@@ -168,6 +168,7 @@ struct lc3d_ctx {
   lc3d::Timer chunk;  // two events used to poll the ICP loop's done flag
   cudaStream_t copy_stream = nullptr;  // H2D / D2H of the host-buffer entry points (overlaps compute)
   cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};  // per-array upload completion (host-buffer ICP)
   cudaStream_t aux_stream = nullptr;  // target index fill, concurrent with the source ordering
   cudaEvent_t ev_aux = nullptr;
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls

@@ -17,6 +17,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <functional>
 
 #include "common.cuh"
 #include "scan_sort.cuh"
@@ -364,7 +365,10 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
   G.ncell = (int64_t)g.dx * g.dy * g.dz;
 }
 
-inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64) {
+// before_gather: called (stream-ordered on ctx->stream) right before the normals are first read,
+// so a caller may still be uploading them while the keys are sorted.
+inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
+                      const std::function<void()>& before_gather = nullptr) {
   const int n = (int)n64;
   if (n == 0) return;  // grid_plan set up the empty grid
   cudaStream_t st = ctx->stream;
@@ -398,6 +402,7 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
   // 5. cell_start = exclusive scan of the cell histogram (ncell+1 entries)
   exclusive_scan_u32(ctx, cell_start, cell_start, G.ncell + 1, ctx->scratch[kScrScan].as<uint32_t>());
   // 6. gather into sorted SoA float4 (finite points come first: sentinel key sorts last)
+  if (before_gather) before_gather();
   LC3D_LAUNCH(ctx, gather_sorted, div_up(n, 256), 256, 0, xyz, nrm, vals, n, G.pts.as<float4>(),
               nrm ? G.nrm.as<float4>() : nullptr, (float4*)nullptr);
   g.cell_start = cell_start;
