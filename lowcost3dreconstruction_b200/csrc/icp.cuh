@@ -1,18 +1,20 @@
 // icp.cuh — the ICP loop of pcl::IterativeClosestPoint::align as driven by
 // pcl_tools/fine_registration.cpp:105-126, entirely on the device.
 //
-// One kernel per iteration (icp_iteration_kernel) fuses
-//   transformCloud (incremental float32 transform of the source, applied at the head
-//     of the NEXT iteration because T_k is only known after the grid-wide reduce),
-//   determineCorrespondences (exact 1-NN + max-distance gate),
-//   the estimator's sums (3x3 cross-covariance for Umeyama/SVD, or the 6x6 normal
-//     equations of point-to-plane LLS) accumulated in fp64: warp shuffles -> shared
-//     memory -> per-block partials -> the last block to finish reduces them in a fixed
-//     order (deterministic), solves (3x3 one-sided Jacobi SVD / 6x6 elimination),
-//     composes final_transformation_ and runs DefaultConvergenceCriteria.
-// The host enqueues max_iterations launches back to back; once the device-side state
-// machine sets `done` the remaining launches return immediately.  No per-iteration
-// host round trip.
+// Two kernels per iteration:
+//   icp_iteration_kernel fuses
+//     transformCloud (incremental float32 transform of the source, applied at the head of
+//       the NEXT iteration because T_k is only known after the grid-wide reduce),
+//     determineCorrespondences (exact 1-NN + max-distance gate, seeded by the previous match),
+//     the estimator's sums (3x3 cross-covariance for Umeyama/SVD, or the 6x6 normal equations
+//       of point-to-plane LLS) in fp64: one butterfly reduce-scatter per warp, one partial row
+//       per warp, no block epilogue;
+//   icp_solve_kernel reduces the warp rows in a fixed order (deterministic), the last block
+//     solves (3x3 one-sided Jacobi SVD / 6x6 elimination, in registers), composes
+//     final_transformation_ and runs DefaultConvergenceCriteria.
+// The chain is launched with programmatic dependent launch; the host enqueues iterations in
+// chunks and polls the device-side `done` flag asynchronously (no per-iteration round trip);
+// once `done` is set the remaining launches return immediately.
 #pragma once
 #include "search.cuh"
 
@@ -22,10 +24,6 @@ namespace lc3d {
 #define LC3D_ICP_THREADS 128
 #endif
 constexpr int kIcpThreads = LC3D_ICP_THREADS;
-#ifndef LC3D_FIT_THREADS
-#define LC3D_FIT_THREADS 256
-#endif
-constexpr int kFitThreads = LC3D_FIT_THREADS;
 constexpr int kNvP2P = 17;     // sum s(3) sum d(3) sum d s^T(9) sum d2(1) count(1)
 constexpr int kNvP2Plane = 29; // JtJ upper(21) Jtr(6) sum d2(1) count(1)
 
