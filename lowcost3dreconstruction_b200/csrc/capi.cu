@@ -301,7 +301,9 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // copied to pinned memory asynchronously, and the host looks at chunk c's flag only after
   // chunk c+1 is already queued — no bubble, no per-iteration round trip, and far fewer no-op
   // launches than enqueueing all max_iterations up front.
-  const int kChunk = want_stats ? p->max_iterations : 4;
+  int chunk_env = 4;
+  if (const char* e = std::getenv("LC3D_CHUNK")) chunk_env = std::max(1, std::atoi(e));
+  const int kChunk = want_stats ? p->max_iterations : chunk_env;
   ctx->pinned[1].ensure(sizeof(int) * (size_t)(p->max_iterations / kChunk + 2));
   int* h_done = ctx->pinned[1].as<int>();
   cudaEvent_t chunk_ev[2] = {ctx->chunk.a, ctx->chunk.b};
