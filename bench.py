@@ -278,9 +278,10 @@ def main():
     alg_bytes = 64.0 * S.n  # whole point-to-plane iteration = 64 B per source point
     achieved = alg_bytes / t_iter_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read+write per launch from profiles/r01_icp_iteration_ncu_full.csv (ncu --set
-                # full, caches flushed per replay): 19.3 MB = the algorithmic bytes, i.e. no DRAM re-reads
-                "traffic": 19.3e6, "kernel": "icp_iteration_kernel<point-to-plane>",
+                # dram__bytes_read+write per launch of a converged iteration from
+                # profiles/r01c_icp_kernels_ncu_full.csv (ncu --set full, caches flushed per replay):
+                # 17.7 MB <= the algorithmic bytes, i.e. no DRAM re-reads (live, the set is L2-resident)
+                "traffic": 17.7e6, "kernel": "icp_iteration_kernel<point-to-plane>",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_iter_s * 1e6,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"}
 
