@@ -616,6 +616,9 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
       hooks.before_target_normals = [&] { upload_finish_normals(ctx, pt); };
       hooks.before_source_normals = [&] { upload_finish_normals(ctx, ps); };
       icp_run(ctx, &tc.a, &tc.b, params, result, outputs, hooks, true);
+      // every staged copy has been consumed on the paths above except in odd output
+      // combinations (normals requested without xyz): never return with a copy in flight
+      if (cs) LC3D_CUDA(cudaStreamSynchronize(cs));
     } catch (...) {
       if (cs) cudaStreamSynchronize(cs);  // no copy may still read the caller's buffers
       throw;
