@@ -385,7 +385,8 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     LC3D_CUDA(cudaMemsetAsync(fq.count, 0, 4, st));
     LC3D_LAUNCH(ctx, icp_fitness_kernel, std::max(1, div_up(n, kIcpThreads)), kIcpThreads, 0, d_state, G.v, X0, Mj, n, d2_all, fq,
                 cfg.stats ? cfg.stats + p->max_iterations : (SearchStats*)nullptr);
-    LC3D_LAUNCH(ctx, icp_fitness_hard_kernel, ctx->num_sms * 8, 128, 0, d_state, G.v, X0, d2_all, fq);
+    LC3D_LAUNCH(ctx, icp_fitness_hard_kernel, ctx->num_sms * (1024 / kHardThreads), kHardThreads, 0, d_state, G.v, X0,
+                d2_all, fq);
     LC3D_LAUNCH(ctx, icp_fitness_reduce_kernel, kFitReduceBlocks, 256, 0, d_state, d2_all, n, partials,
                 fq.count);
   }

@@ -541,7 +541,10 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
 // Second kernel of an iteration: block v reduces estimator value v over all warp rows in a
 // fixed order (deterministic), the last block to finish (atomic ticket) solves, composes the
 // pose and runs the convergence test.  grid = NV blocks.
-constexpr int kSolveThreads = 512;
+#ifndef LC3D_SOLVE_THREADS
+#define LC3D_SOLVE_THREADS 512
+#endif
+constexpr int kSolveThreads = LC3D_SOLVE_THREADS;
 template <int MODE>
 __global__ void __launch_bounds__(kSolveThreads)
     icp_solve_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const double* __restrict__ partials,
@@ -644,7 +647,11 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   if (i < n) d2_all[i] = (active && !deferred && b.j >= 0) ? b.d2 : -1.0f;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef LC3D_HARD_THREADS
+#define LC3D_HARD_THREADS 128
+#endif
+constexpr int kHardThreads = LC3D_HARD_THREADS;
+__global__ void __launch_bounds__(kHardThreads)
     icp_fitness_hard_kernel(const IcpState* __restrict__ st, const __grid_constant__ GridDev g,
                             const float4* __restrict__ src0, float* __restrict__ d2_all,
                             const FitQueue fq) {
