@@ -76,3 +76,19 @@ def test_host_cloud_views():
     assert hc.struct.rgba - hc.struct.xyz == 32 and hc.struct.curvature - hc.struct.xyz == 36
     hc2 = HostCloud(np.arange(6, dtype=np.float64).reshape(2, 3))
     assert hc2.xyz.dtype == np.float32 and hc2.struct.normal is None
+
+
+def test_documented_tunables_exist_in_source():
+    """INTEGRATION.md's table of LC3D_* environment variables must match what the code reads."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    table = doc[doc.index("## Tunables"):doc.index("## Semantics worth knowing")]
+    documented = set(re.findall(r"`(LC3D_[A-Z_]+)`", table))
+    src = ""
+    for d, exts in (("lowcost3dreconstruction_b200/csrc", (".cu", ".cuh", ".inc")), ("lowcost3dreconstruction_b200", (".py",))):
+        for f in os.listdir(os.path.join(root, d)):
+            if f.endswith(exts):
+                src += open(os.path.join(root, d, f)).read()
+    read_by_code = set(re.findall(r'getenv\("(LC3D_[A-Z_]+)"\)', src)) | set(re.findall(r'environ\.get\("(LC3D_[A-Z_]+)"', src))
+    assert documented == read_by_code, (sorted(documented - read_by_code), sorted(read_by_code - documented))
