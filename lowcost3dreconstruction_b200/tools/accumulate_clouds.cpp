@@ -9,7 +9,7 @@
 using namespace lc3d_tools;
 
 int main(int argc, char* argv[]) {
-  try {
+  return run_tool([&]() -> int {
     Options opt("Options");
     opt.flag("help", 'h', "Print help message")
         .value("input", 'i', "Input cloud file (.ply)")
@@ -93,10 +93,5 @@ int main(int argc, char* argv[]) {
         throw std::runtime_error("Couldn't write " + out_name + "_negative.ply");
     }
     return 0;
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-  } catch (...) {
-    std::cerr << "An unknown error has occurred." << std::endl;
-  }
-  return -1;
+  });
 }

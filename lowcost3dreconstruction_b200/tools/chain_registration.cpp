@@ -30,7 +30,7 @@ void mat_mul(const double* a, const double* b, double* o) {
 }  // namespace
 
 int main(int argc, char* argv[]) {
-  try {
+  return run_tool([&]() -> int {
     Options opt("Options");
     opt.flag("help", 'h', "Print help message")
         .value("num_captures", 'n', "Number of views: <dir>/0.ply .. <dir>/(n-1).ply")
@@ -144,10 +144,5 @@ int main(int argc, char* argv[]) {
       }
     }
     return 0;
-  } catch (const OptionError& e) {
-    std::cerr << "ERROR: " << e.what() << std::endl;
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-  }
-  return -1;
+  }, true);
 }

@@ -192,6 +192,23 @@ inline lc3d_cloud as_lc3d(const Cloud& c, bool normals = true) {
   return v;
 }
 
+// main() scaffold shared by the tools.  Like the reference mains: whatever goes wrong is one
+// line on stderr and exit status -1; option-parser errors get the "ERROR: " prefix where the
+// reference tool catches them separately (fine_registration).
+template <typename Body>
+int run_tool(Body&& body, bool prefix_option_errors = false) {
+  try {
+    return body();
+  } catch (const OptionError& e) {
+    std::cerr << (prefix_option_errors ? "ERROR: " : "") << e.what() << std::endl;
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << std::endl;
+  } catch (...) {
+    std::cerr << "An unknown error has occurred." << std::endl;
+  }
+  return -1;
+}
+
 struct Ctx {
   lc3d_ctx* h = nullptr;
   Ctx() {

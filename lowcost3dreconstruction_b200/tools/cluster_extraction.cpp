@@ -8,7 +8,7 @@
 using namespace lc3d_tools;
 
 int main(int argc, char* argv[]) {
-  try {
+  return run_tool([&]() -> int {
     Options opt("Options");
     opt.flag("help", 'h', "Print help message")
         .value("input", 'i', "Input file (.ply)")
@@ -81,10 +81,5 @@ int main(int argc, char* argv[]) {
         throw std::runtime_error("Couldn't write " + out_name + "_outliers.ply");
     }
     return 0;
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-  } catch (...) {
-    std::cerr << "An unknown error has occurred." << std::endl;
-  }
-  return -1;
+  });
 }

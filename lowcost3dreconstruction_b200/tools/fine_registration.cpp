@@ -8,13 +8,13 @@
 using namespace lc3d_tools;
 
 namespace {
-struct Usage {
-  std::string msg;
+struct Usage : std::runtime_error {
+  using std::runtime_error::runtime_error;
 };
 }  // namespace
 
 int main(int argc, char* argv[]) {
-  try {
+  return run_tool([&]() -> int {
     Options opt("Options");
     opt.flag("help", 'h', "Print help message")
         .value("input", 'i', "Input cloud file (.ply)")
@@ -101,12 +101,5 @@ int main(int argc, char* argv[]) {
       std::fclose(f);
     }
     return 0;
-  } catch (const OptionError& e) {
-    std::cerr << "ERROR: " << e.what() << std::endl;
-  } catch (const Usage& u) {
-    std::cerr << u.msg << std::endl;
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-  }
-  return -1;
+  }, true);
 }

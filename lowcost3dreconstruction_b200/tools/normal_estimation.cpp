@@ -5,7 +5,7 @@
 using namespace lc3d_tools;
 
 int main(int argc, char* argv[]) {
-  try {
+  return run_tool([&]() -> int {
     Options opt("Options");
     opt.flag("help", 'h', "Print help message")
         .value("input", 'i', "Input file (.ply)")
@@ -54,10 +54,5 @@ int main(int argc, char* argv[]) {
     }
     if (save_ply_binary(opt.str("output"), cloud) != 0) throw std::runtime_error("Couldn't write " + opt.str("output"));
     return 0;
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-  } catch (...) {
-    std::cerr << "An unknown error has occurred." << std::endl;
-  }
-  return -1;
+  });
 }

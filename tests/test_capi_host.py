@@ -86,7 +86,8 @@ def test_documented_tunables_exist_in_source():
     table = doc[doc.index("## Tunables"):doc.index("## Semantics worth knowing")]
     documented = set(re.findall(r"`(LC3D_[A-Z_]+)`", table))
     src = ""
-    for d, exts in (("lowcost3dreconstruction_b200/csrc", (".cu", ".cuh", ".inc")), ("lowcost3dreconstruction_b200", (".py",))):
+    for d, exts in (("lowcost3dreconstruction_b200/csrc", (".cu", ".cuh", ".inc")), ("lowcost3dreconstruction_b200", (".py",)),
+                    ("lowcost3dreconstruction_b200/tools", (".cpp", ".hpp"))):
         for f in os.listdir(os.path.join(root, d)):
             if f.endswith(exts):
                 src += open(os.path.join(root, d, f)).read()
