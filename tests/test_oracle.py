@@ -274,3 +274,42 @@ def test_euclidean_clusters_against_connected_components():
     two = np.array([[0, 0, 0], [0.5, 0, 0]], np.float32)
     assert orc.euclidean_clusters(two, 0.5, 1, 2)[1].tolist() == [1, 1]
     assert orc.euclidean_clusters(two, 0.5000001, 1, 2)[1].tolist() == [2]
+
+
+def test_single_iteration_estimators_against_numpy(pair):
+    """One ICP iteration of the oracle vs an independent numpy restatement of the published
+    estimators: Umeyama without scale, and the point-to-plane LLS
+    (J = [n x s-ish cross terms, n], r = n.(d - s), x = (J^T J)^-1 J^T r, R = Rz Ry Rx)."""
+    src, tgt = pair
+    nrm, _ = orc.normals(tgt, 15)
+    ok = np.isfinite(nrm).all(1)
+    tgt, nrm = tgt[ok], nrm[ok]
+    max_d = 0.02
+    tree = orc.KdTree(tgt)
+    idx, d2 = tree.nn(src, max_d)
+    m = idx >= 0
+    s = src[m].astype(np.float64)
+    d = tgt[idx[m]].astype(np.float64)
+    n = nrm[idx[m]].astype(np.float64)
+    # --- point-to-point: Umeyama / Kabsch
+    cnt, T = tree.one_iteration(src, tgt, max_d, 0)
+    assert cnt == int(m.sum())
+    mu_s, mu_d = s.mean(0), d.mean(0)
+    S = (d - mu_d).T @ (s - mu_s) / len(s)
+    U, _, Vt = np.linalg.svd(S)
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+    R = U @ D @ Vt
+    t = mu_d - R @ mu_s
+    assert np.abs(T[:3, :3] - R).max() < 2e-6 and np.abs(T[:3, 3] - t).max() < 2e-6
+    # --- point-to-plane LLS
+    cnt, T = tree.one_iteration(src, HostCloud(tgt, normal=nrm), max_d, 1)
+    assert cnt == int(m.sum())
+    J = np.concatenate([np.cross(s, n), n], axis=1)
+    r = np.einsum("ij,ij->i", n, d - s)
+    x = np.linalg.solve(J.T @ J, J.T @ r)
+    al, be, ga = x[:3]
+    Rx = np.array([[1, 0, 0], [0, np.cos(al), -np.sin(al)], [0, np.sin(al), np.cos(al)]])
+    Ry = np.array([[np.cos(be), 0, np.sin(be)], [0, 1, 0], [-np.sin(be), 0, np.cos(be)]])
+    Rz = np.array([[np.cos(ga), -np.sin(ga), 0], [np.sin(ga), np.cos(ga), 0], [0, 0, 1]])
+    assert np.abs(T[:3, :3] - Rz @ Ry @ Rx).max() < 2e-6 and np.abs(T[:3, 3] - x[3:]).max() < 2e-6
+    assert np.array_equal(T[3], [0, 0, 0, 1])
