@@ -313,3 +313,25 @@ def test_single_iteration_estimators_against_numpy(pair):
     Rz = np.array([[np.cos(ga), -np.sin(ga), 0], [np.sin(ga), np.cos(ga), 0], [0, 0, 1]])
     assert np.abs(T[:3, :3] - Rz @ Ry @ Rx).max() < 2e-6 and np.abs(T[:3, 3] - x[3:]).max() < 2e-6
     assert np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_convergence_criteria_replayed_from_the_iteration_log(pair):
+    """DefaultConvergenceCriteria replayed in numpy on the oracle's per-iteration
+    log (correspondence count, mse): the loop must stop at the FIRST iteration whose relative
+    mse change drops below euclidean_fitness_epsilon, and not before."""
+    src, tgt = pair
+    for eps in (1e-3, 1e-4, 1e-2):
+        # transformation_epsilon tiny: the TRANSFORM exit (|t|^2 <= eps) must not pre-empt the mse test
+        r = orc.icp_align(src, tgt, 0.02, 50, euclidean_fitness_epsilon=eps, transformation_epsilon=1e-30)
+        mse = r["log"][:, 1]
+        assert r["state"] == 4 and len(mse) == r["iterations"]
+        rel = np.abs(np.diff(mse)) / mse[:-1]
+        stop = np.flatnonzero(rel < eps)
+        assert len(stop) and stop[0] + 2 == r["iterations"]       # iteration k+1 sees |mse_k+1 - mse_k| / mse_k
+        assert (np.abs(np.diff(mse))[: stop[0]] >= 1e-12).all()    # the absolute test never fired earlier
+        assert r["last_mse"] == mse[-1] and r["last_correspondences"] == r["log"][-1, 0]
+    # mse is the mean SQUARED kd-tree distance of the correspondences found before the update
+    idx, d2 = orc.KdTree(tgt).nn(src, 0.02)
+    r = orc.icp_align(src, tgt, 0.02, 1)
+    assert r["last_correspondences"] == (idx >= 0).sum()
+    assert abs(r["last_mse"] - d2[idx >= 0].astype(np.float64).mean()) <= 1e-12 * r["last_mse"]
