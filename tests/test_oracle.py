@@ -335,3 +335,16 @@ def test_convergence_criteria_replayed_from_the_iteration_log(pair):
     r = orc.icp_align(src, tgt, 0.02, 1)
     assert r["last_correspondences"] == (idx >= 0).sum()
     assert abs(r["last_mse"] - d2[idx >= 0].astype(np.float64).mean()) <= 1e-12 * r["last_mse"]
+
+
+def test_fitness_score_is_the_unbounded_mean_nn_distance(pair):
+    """getFitnessScore: every source point counts, no max-distance gate; the
+    registered cloud is ONE application of the composed transform to the original source."""
+    src, tgt = pair
+    r = orc.icp_align(src, tgt, 0.02, 50, want_registered=True)
+    reg = r["registered_xyz"]
+    xyz, _ = orc.transform(src, r["transformation"])
+    assert np.array_equal(reg, xyz)
+    d2 = cKDTree(tgt.astype(np.float64)).query(reg.astype(np.float64))[0] ** 2
+    assert abs(r["fitness"] - d2.mean()) <= 1e-6 * d2.mean()
+    assert (d2 > 0.02 ** 2).any()          # the sum really includes points beyond the gate
