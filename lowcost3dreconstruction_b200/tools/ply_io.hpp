@@ -15,6 +15,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace lc3d_tools {
@@ -292,6 +293,81 @@ inline int load_ply(const std::string& path, Cloud& cloud, std::string* err = nu
         cur = ascii.data();
         ascii_end = ascii.data() + ascii.size();
         ascii_loaded = true;
+      }
+      // Large vertex elements without list properties are parsed by several threads: the token
+      // starts of each byte chunk are counted first, so every thread knows which vertex its
+      // chunk begins in and parses a contiguous, vertex-aligned range straight into the output.
+      bool has_list = false;
+      for (const Property& p : e.props) has_list = has_list || p.is_list;
+      const size_t np = e.props.size();
+      unsigned nthreads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+      if (const char* env = std::getenv("LC3D_PLY_THREADS")) nthreads = (unsigned)std::max(1, std::atoi(env));
+      if (is_vertex && !has_list && np > 0 && nthreads > 1 && e.count >= (size_t)100000) {
+        const size_t bytes = (size_t)(ascii_end - cur);
+        const size_t chunk = (bytes + nthreads - 1) / nthreads;
+        auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; };
+        std::vector<size_t> tok_before(nthreads + 1, 0);
+        {
+          std::vector<std::thread> th;
+          for (unsigned k = 0; k < nthreads; ++k)
+            th.emplace_back([&, k] {
+              const char* b = cur + std::min(bytes, (size_t)k * chunk);
+              const char* f = cur + std::min(bytes, (size_t)(k + 1) * chunk);
+              size_t n = 0;
+              bool prev_ws = b == cur ? true : is_ws(b[-1]);
+              for (const char* q = b; q < f; ++q) {
+                const bool ws = is_ws(*q);
+                n += (!ws && prev_ws) ? 1 : 0;
+                prev_ws = ws;
+              }
+              tok_before[k + 1] = n;
+            });
+          for (auto& t : th) t.join();
+        }
+        for (unsigned k = 0; k < nthreads; ++k) tok_before[k + 1] += tok_before[k];
+        if (tok_before[nthreads] < e.count * np) return fail("truncated PLY data");
+        cloud.points.resize(e.count);
+        std::vector<const char*> end_ptr(nthreads, nullptr);
+        std::vector<char> bad(nthreads, 0);
+        {
+          std::vector<std::thread> th;
+          for (unsigned k = 0; k < nthreads; ++k)
+            th.emplace_back([&, k] {
+              const size_t v0 = std::min(e.count, (tok_before[k] + np - 1) / np);
+              const size_t v1 = k + 1 == nthreads ? e.count : std::min(e.count, (tok_before[k + 1] + np - 1) / np);
+              if (v0 >= v1) return;
+              const char* q = cur + std::min(bytes, (size_t)k * chunk);
+              // a token straddling the chunk start belongs to the previous chunk
+              if (q != cur && !is_ws(q[-1]))
+                while (q < ascii_end && !is_ws(*q)) ++q;
+              double v;
+              for (size_t skip = v0 * np - tok_before[k]; skip > 0; --skip)
+                if (!(q = parse_number(q, ascii_end, &v))) {
+                  bad[k] = 1;
+                  return;
+                }
+              for (size_t i = v0; i < v1; ++i) {
+                Point pt{};
+                pt.w = 1.0f;
+                pt.rgba = 0xff000000u;
+                for (size_t j = 0; j < np; ++j) {
+                  if (!(q = parse_number(q, ascii_end, &v))) {
+                    bad[k] = 1;
+                    return;
+                  }
+                  assign(pt, slots[j], v, e.props[j].type, nullptr);
+                }
+                cloud.points[i] = pt;
+              }
+              end_ptr[k] = q;
+            });
+          for (auto& t : th) t.join();
+        }
+        for (unsigned k = 0; k < nthreads; ++k) {
+          if (bad[k]) return fail("truncated PLY data");
+          if (end_ptr[k]) cur = end_ptr[k];  // ranges are ascending: the last one ends the element
+        }
+        continue;
       }
       for (size_t i = 0; i < e.count; ++i) {
         Point pt{};

@@ -125,3 +125,50 @@ def test_ascii_number_parser_is_exact(tmp_path):
         want = np.array([float(t) for t in vals.reshape(-1)], dtype=np.float64).astype(np.float32)
     assert np.array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
     assert np.array_equal(np.isnan(got), np.isnan(want))
+
+
+def test_parallel_ascii_parse_matches_sequential(tmp_path):
+    """Vertex elements of >= 100k points are parsed by several threads (token-count prefix sums
+    give every thread a vertex-aligned range): the result must be byte-identical to the
+    single-thread parse, whatever the whitespace layout, and the elements after it must still parse."""
+    rng = np.random.default_rng(5)
+    n = 150_001
+    xyz = np.round(rng.normal(0, 300, (n, 3)), 6)
+    nrm = np.round(rng.normal(0, 1, (n, 3)), 6)
+    rgb = rng.integers(0, 256, (n, 3))
+    src = str(tmp_path / "big.ply")
+    seps = [" ", "  ", "\t", " \t "]
+    with open(src, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "property float nx\nproperty float ny\nproperty float nz\nproperty uchar red\nproperty uchar green\n"
+                "property uchar blue\nelement face 2\nproperty list uchar int vertex_index\nend_header\n" % n)
+        lines = []
+        for i in range(n):
+            s = seps[i % 4]
+            vals = ["%.6f" % v for v in xyz[i]] + ["%.6f" % v for v in nrm[i]] + ["%d" % v for v in rgb[i]]
+            eol = "\r\n" if i % 7 == 0 else ("\n\n" if i % 1001 == 0 else "\n")
+            # every 5000th vertex is split over two lines: the parser is token-based, not line-based
+            if i % 5000 == 17:
+                lines.append(s.join(vals[:4]) + "\n" + s.join(vals[4:]) + eol)
+            else:
+                lines.append(s.join(vals) + eol)
+        f.write("".join(lines))
+        f.write("3 0 1 2\n3 2 1 0\n")
+    outs = {}
+    for threads in ("1", "2", "7", "16"):
+        dst = str(tmp_path / f"o{threads}.ply")
+        p = subprocess.run([CONVERT, src, dst], capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, LC3D_PLY_THREADS=threads))
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.startswith("points %d normals 1 color 1" % n)
+        outs[threads] = open(dst, "rb").read()
+    assert outs["1"] == outs["2"] == outs["7"] == outs["16"]
+    pts = plyutil.read_pcl_binary(str(tmp_path / "o7.ply"))
+    assert np.array_equal(pts["xyz"], xyz.astype(np.float32)) and np.array_equal(pts["rgb"], rgb.astype(np.uint8))
+    # truncated body: every thread count reports it
+    data = open(src).read()
+    open(src, "w").write(data[: len(data) // 2])
+    for threads in ("1", "7"):
+        p = subprocess.run([CONVERT, src, str(tmp_path / "t.ply")], capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, LC3D_PLY_THREADS=threads))
+        assert p.returncode != 0 and "truncated PLY data" in p.stderr
