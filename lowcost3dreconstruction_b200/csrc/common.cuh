@@ -162,7 +162,7 @@ struct lc3d_ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = lc3d::kNumSmsB200;
-  lc3d::DevBuf scratch[40];  // grow-only scratch arena, slots named by the users
+  lc3d::DevBuf scratch[64];  // grow-only scratch arena, slots named by the users
   lc3d::PinnedBuf pinned[2];
   lc3d::Timer tm[6];
   lc3d::Timer chunk;  // two events used to poll the ICP loop's done flag
@@ -172,6 +172,7 @@ struct lc3d_ctx {
   cudaStream_t aux_stream = nullptr;  // target index fill, concurrent with the source ordering
   cudaEvent_t ev_aux = nullptr;
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
+  bool rowtab_ready = false;   // row-offset table of the ICP search uploaded (icp2.cuh)
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
 };
 

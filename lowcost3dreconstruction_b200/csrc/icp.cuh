@@ -58,6 +58,11 @@ struct IcpConfig {
   int dump_iteration;
   int mode;
   SearchStats* stats;  // per-iteration search statistics (LC3D_STATS=1) or null
+  // icp2.cuh: search-ball policy of the triangle-inequality kernel
+  float r_cap;     // sqrt(gate_ext) rounded up: no search reaches farther (+inf without a gate)
+  float mu0;       // runner-up margin of iteration 0 (the first motion is large: 0)
+  float mu_min, mu_max, mu_kappa;  // later: margin = clamp(kappa * last motion of the point, min, max)
+  float tab_wmax;  // widest ball (cells) served by the row-offset table
 };
 
 __global__ void icp_state_init(IcpState* st) {
@@ -615,7 +620,7 @@ struct FitQueue {
 
 __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
     icp_fitness_kernel(const IcpState* __restrict__ st, const __grid_constant__ GridDev g,
-                       const float4* __restrict__ src0, const int* __restrict__ Mj, int n,
+                       const float4* __restrict__ src0, const int* __restrict__ Mj, int mj_stride, int n,
                        float* __restrict__ d2_all, const FitQueue fq, SearchStats* stats) {
   __shared__ float sT[16];
   if (threadIdx.x < 16) sT[threadIdx.x] = st->Tfinal[threadIdx.x];
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   const float z = xform_row(sT, 2, q.x, q.y, q.z);
   // seeded by the last iteration's matches (the final pose differs from the incremental one
   // only by float rounding), unbounded: every source point counts
-  const int seed_j = (active && Mj) ? Mj[i] : -1;
+  const int seed_j = (active && Mj) ? Mj[(size_t)i * mj_stride] : -1;
   bool deferred = false;
   const Best b = nn_search_seeded<true>(g, active, x, y, z, INFINITY, seed_j, stats, &deferred);
   const unsigned dm = __ballot_sync(0xffffffffu, deferred);
