@@ -9,8 +9,6 @@
 #include "cluster.cuh"
 #include "grid.cuh"
 #include "icp.cuh"
-#include "icp2.cuh"
-#include "icp3.cuh"
 #include "knn.cuh"
 #include "scan_sort.cuh"
 #include "search.cuh"
@@ -27,7 +25,6 @@ enum {
   kScrRawA = kScrGridEnd, kScrRawB, kScrRawC, kScrRawD, kScrSrcSorted, kScrSrcWork, kScrState, kScrPartials, kScrOutA,
   kScrOutB, kScrDumpIdx, kScrDumpD2, kScrBound, kScrPrevMatch, kScrMisc, kScrMisc2, kScrMisc3,
   kScrSrcSort0, kScrSrcSort1, kScrSrcSort2, kScrSrcSort3, kScrSrcSort4, kScrSrcSort5,  // private sort scratch
-  kScrMatchBound, kScrRowTab, kScrLists, kScrListCnt,
   kScrEnd
 };
 static_assert(kScrEnd <= 64, "scratch slots");
@@ -213,8 +210,10 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
       ~StreamSwap() { c->stream = saved; }
     } swap{ctx, ctx->stream};
     if (two_streams) ctx->stream = ctx->aux_stream;
+    const float gate0 = gate_from_distance(p->max_correspondence_distance);
     grid_fill(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr, tgt->n,
-              hooks.before_target_normals);
+              hooks.before_target_normals,
+              std::isinf(gate0) || std::getenv("LC3D_NO_OCC") ? 0.0 : (double)std::nextafterf(std::sqrt(gate0), INFINITY));
     if (two_streams) LC3D_CUDA(cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
   }
   if (before_source) before_source();
@@ -263,42 +262,6 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     cfg.slack_floor = (float)(1e-4 * (r + margin));
     cfg.margin_slack = std::isfinite(ge) ? (float)(margin * 0.9999) : 0.0f;
     if (!std::isfinite(ge)) cfg.slack_floor = INFINITY;
-  }
-  // ---- second-generation iteration kernel (icp2.cuh): ball policy + row-offset table ----
-  const bool v1 = std::getenv("LC3D_ICP_V1") != nullptr;
-  auto envf = [](const char* name, double dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atof(e) : dflt;
-  };
-  {
-    const double spacing = (double)G.v.c / cell_factor_env();  // estimated point spacing of the target
-    cfg.r_cap = std::isinf(cfg.gate_ext) ? INFINITY : std::nextafterf(std::sqrt(cfg.gate_ext), INFINITY);
-    cfg.mu0 = (float)(envf("LC3D_MU0", 0.0) * spacing);
-    cfg.mu_min = (float)(envf("LC3D_MU_MIN", 0.3) * spacing);
-    cfg.mu_max = (float)(envf("LC3D_MU_MAX", 1.5) * spacing);
-    cfg.mu_kappa = (float)envf("LC3D_MU_KAPPA", 2.0);
-    cfg.tab_wmax = (float)std::min(envf("LC3D_COOP_MAXW", 8.0), (double)kTabW - 1.5);
-  }
-  if (!ctx->rowtab_ready) {
-    std::vector<int2> tab;
-    build_row_table(tab);
-    ctx->scratch[kScrRowTab].ensure(tab.size() * sizeof(int2));
-    LC3D_CUDA(cudaMemcpyAsync(ctx->scratch[kScrRowTab].p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    LC3D_CUDA(cudaStreamSynchronize(st));  // `tab` is a stack object
-    ctx->rowtab_ready = true;
-  }
-  const int2* rowtab = ctx->scratch[kScrRowTab].as<int2>();
-  ctx->scratch[kScrMatchBound].ensure((size_t)n * 8 + 16);
-  int2* MB = ctx->scratch[kScrMatchBound].as<int2>();
-  const int nblk2 = std::max(1, div_up(n, kI2Threads));
-  const bool v2 = std::getenv("LC3D_ICP_V2") != nullptr;
-  Icp3Lists lists{nullptr, nullptr};
-  if (!v1 && !v2 && envf("LC3D_LISTS", 1.0) != 0.0) {
-    ctx->scratch[kScrLists].ensure((size_t)n * kListK * 4 + 16);
-    ctx->scratch[kScrListCnt].ensure((size_t)n + 16);
-    lists.lst = ctx->scratch[kScrLists].as<int>();
-    lists.cnt = ctx->scratch[kScrListCnt].as<unsigned char>();
-    LC3D_CUDA(cudaMemsetAsync(lists.cnt, 0, (size_t)n + 16, st));
   }
   cfg.max_iterations = p->max_iterations;
   cfg.rot_thr = 1.0 - p->transformation_epsilon;
@@ -351,47 +314,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
     // programmatic dependent launch: each kernel of the chain is staged while its predecessor
     // drains (the kernels call pdl_wait() before reading anything the predecessor wrote)
-    if (!v1 && !v2) {
-      if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
-        if (want_stats)
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter3_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk2, kI3Threads, d_state, cfg,
-                          G.v, X, MB, lists, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        else
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter3_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk2, kI3Threads, d_state, cfg,
-                          G.v, X, MB, lists, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
-                        partials, nblk2, reduced);
-      } else {
-        if (want_stats)
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter3_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk2, kI3Threads, d_state, cfg,
-                          G.v, X, MB, lists, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        else
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter3_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk2, kI3Threads, d_state, cfg,
-                          G.v, X, MB, lists, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
-                        partials, nblk2, reduced);
-      }
-    } else if (!v1) {
-      if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
-        if (want_stats)
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter2_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk2, kI2Threads, d_state, cfg,
-                          G.v, X, MB, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        else
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter2_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk2, kI2Threads, d_state, cfg,
-                          G.v, X, MB, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
-                        partials, nblk2, reduced);
-      } else {
-        if (want_stats)
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter2_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk2, kI2Threads, d_state, cfg,
-                          G.v, X, MB, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        else
-          LC3D_LAUNCH_PDL(ctx, pdl, (icp_iter2_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk2, kI2Threads, d_state, cfg,
-                          G.v, X, MB, n, partials, d_dump_idx, d_dump_d2, rowtab);
-        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
-                        partials, nblk2, reduced);
-      }
-    } else if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
+    if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
       if (want_stats)
         LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk, kIcpThreads, d_state,
                         cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
@@ -399,7 +322,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
         LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, d_state,
                         cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
-                      partials, nwarps_icp, reduced);
+                      partials, nblk, reduced);
     } else {
       if (want_stats)
         LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk, kIcpThreads, d_state,
@@ -408,7 +331,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
         LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, d_state,
                         cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
       LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
-                      partials, nwarps_icp, reduced);
+                      partials, nblk, reduced);
     }
   };
   {
@@ -463,7 +386,7 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     fq.count = reinterpret_cast<unsigned*>(fq.seed + n);
     LC3D_CUDA(cudaMemsetAsync(fq.count, 0, 4, st));
     LC3D_LAUNCH(ctx, icp_fitness_kernel, std::max(1, div_up(n, kIcpThreads)), kIcpThreads, 0, d_state, G.v, X0,
-                v1 ? Mj : reinterpret_cast<const int*>(MB), v1 ? 1 : 2, n, d2_all, fq,
+                Mj, 1, n, d2_all, fq,
                 cfg.stats ? cfg.stats + p->max_iterations : (SearchStats*)nullptr);
     LC3D_LAUNCH(ctx, icp_fitness_hard_kernel, ctx->num_sms * (1024 / kHardThreads), kHardThreads, 0, d_state, G.v, X0,
                 d2_all, fq);

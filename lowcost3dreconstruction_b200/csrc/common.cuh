@@ -172,7 +172,6 @@ struct lc3d_ctx {
   cudaStream_t aux_stream = nullptr;  // target index fill, concurrent with the source ordering
   cudaEvent_t ev_aux = nullptr;
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
-  bool rowtab_ready = false;   // row-offset table of the ICP search uploaded (icp2.cuh)
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
 };
 

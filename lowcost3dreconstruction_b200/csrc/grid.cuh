@@ -46,11 +46,15 @@ struct GridDev {
   const uint32_t* coarse_cnt;
   const float4* pts;
   const float4* nrm;
+  // dilated occupancy bits at c-cell resolution (x packed 32 cells per word), or null: a clear
+  // bit proves that no indexed point lies within (occ_r - 0.01) * c of ANY position inside the cell
+  const uint32_t* occ;
+  int occ_wx, occ_r;
 };
 
 struct Grid {
   GridDev v{};
-  DevBuf cell_start, coarse_cnt, pts, nrm;
+  DevBuf cell_start, coarse_cnt, pts, nrm, occ_raw, occ;
   int64_t ncell = 0;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   void release() {
@@ -58,6 +62,8 @@ struct Grid {
     coarse_cnt.release();
     pts.release();
     nrm.release();
+    occ_raw.release();
+    occ.release();
   }
 };
 
@@ -195,7 +201,8 @@ __device__ __forceinline__ float cell_coord(float v, float o, float inv_c) {
 __global__ void __launch_bounds__(256)
     grid_keys(const float4* __restrict__ p, int n, GridDev g, uint32_t ncell,
               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-              uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ coarse_cnt) {
+              uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ coarse_cnt,
+              uint32_t* __restrict__ occ_bits = nullptr, int occ_wx = 0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = p[i];
@@ -219,9 +226,45 @@ __global__ void __launch_bounds__(256)
       const unsigned peers = __match_any_sync(act, ck);
       if (lane == __ffs(peers) - 1) atomicAdd(&coarse_cnt[ck], (uint32_t)__popc(peers));
     }
+    if (occ_bits) {
+      const int cx = ix >> g.xs_shift;
+      const int word = (iz * g.dy + iy) * occ_wx + (cx >> 5);
+      const uint32_t m = 1u << (cx & 31);
+      const unsigned peers = __match_any_sync(act, word);
+      const uint32_t combined = __reduce_or_sync(peers, m);
+      if (lane == __ffs(peers) - 1 && (occ_bits[word] & combined) != combined) atomicOr(&occ_bits[word], combined);
+    }
   }
   keys[i] = key;
   vals[i] = (uint32_t)i;
+}
+
+// Box dilation (Chebyshev radius r cells) of the occupancy bits: out bit = OR of all bits within r cells.
+__global__ void __launch_bounds__(256)
+    occ_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int wx, int dy, int dz, int r) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wx * dy * dz) return;
+  const int w = idx % wx, y = (idx / wx) % dy, z = idx / (wx * dy);
+  uint32_t acc = 0;
+  for (int zz = max(z - r, 0); zz <= min(z + r, dz - 1); ++zz)
+    for (int yy = max(y - r, 0); yy <= min(y + r, dy - 1); ++yy) {
+      const uint32_t* row = in + (size_t)(zz * dy + yy) * wx;
+      const uint32_t a = row[w], l = w > 0 ? row[w - 1] : 0u, h = w + 1 < wx ? row[w + 1] : 0u;
+      acc |= a;
+      for (int k = 1; k <= r; ++k) acc |= (a << k) | (l >> (32 - k)) | (a >> k) | (h << (32 - k));
+    }
+  out[idx] = acc;
+}
+
+// true: no indexed point within (occ_r - 0.01) * c of the query (proven by the dilated occupancy)
+__device__ __forceinline__ bool occ_proves_empty(const GridDev& g, int ix, int iy, int iz) {
+  if (!g.occ) return false;
+  const int cx = ix >> g.xs_shift, ncx = g.dx >> g.xs_shift;
+  if ((unsigned)cx < (unsigned)ncx && (unsigned)iy < (unsigned)g.dy && (unsigned)iz < (unsigned)g.dz)
+    return ((__ldg(&g.occ[(size_t)(iz * g.dy + iy) * g.occ_wx + (cx >> 5)]) >> (cx & 31)) & 1u) == 0u;
+  // outside the grid: Chebyshev distance (cells) to the grid box
+  const int ox = max(max(-cx, cx - (ncx - 1)), 0), oy = max(max(-iy, iy - (g.dy - 1)), 0), oz = max(max(-iz, iz - (g.dz - 1)), 0);
+  return max(ox, max(oy, oz)) > g.occ_r;
 }
 
 __global__ void __launch_bounds__(256)
@@ -368,7 +411,7 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
 // before_gather: called (stream-ordered on ctx->stream) right before the normals are first read,
 // so a caller may still be uploading them while the keys are sorted.
 inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
-                      const std::function<void()>& before_gather = nullptr) {
+                      const std::function<void()>& before_gather = nullptr, double occ_reach = 0.0) {
   const int n = (int)n64;
   if (n == 0) return;  // grid_plan set up the empty grid
   cudaStream_t st = ctx->stream;
@@ -391,8 +434,31 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
       std::max(scan_scratch_bytes(G.ncell + 2), scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile))) + 64);
   uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
   uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
+  // dilated occupancy (rejects queries with nothing within occ_reach in O(1)): only for small radii
+  g.occ = nullptr;
+  g.occ_wx = g.occ_r = 0;
+  uint32_t* occ_raw = nullptr;
+  int occ_r = 0;
+  const int occ_wx = ((g.dx >> g.xs_shift) + 31) >> 5;
+  const size_t occ_words = (size_t)occ_wx * g.dy * g.dz;
+  if (occ_reach > 0.0 && std::isfinite(occ_reach)) occ_r = (int)std::ceil(occ_reach / (double)g.c + 0.02);
+  if (occ_r >= 1 && occ_r <= 4 && occ_words <= ((size_t)1 << 24)) {
+    G.occ_raw.ensure(occ_words * 4);
+    G.occ.ensure(occ_words * 4);
+    occ_raw = G.occ_raw.as<uint32_t>();
+    LC3D_CUDA(cudaMemsetAsync(occ_raw, 0, occ_words * 4, st));
+  } else {
+    occ_r = 0;
+  }
   LC3D_LAUNCH(ctx, grid_keys, div_up(n, 256), 256, 0, xyz, n, g, (uint32_t)G.ncell, keys, vals,
-              cell_start, G.coarse_cnt.as<uint32_t>());
+              cell_start, G.coarse_cnt.as<uint32_t>(), occ_raw, occ_wx);
+  if (occ_raw) {
+    LC3D_LAUNCH(ctx, occ_dilate, div_up((int64_t)occ_words, 256), 256, 0, occ_raw, G.occ.as<uint32_t>(), occ_wx, g.dy, g.dz,
+                occ_r);
+    g.occ = G.occ.as<uint32_t>();
+    g.occ_wx = occ_wx;
+    g.occ_r = occ_r;
+  }
   // 4. stable radix sort of (cell id, point index)
   SortScratch ss{ctx->scratch[kScrKeysAlt].as<uint32_t>(), ctx->scratch[kScrValsAlt].as<uint32_t>(),
                  ctx->scratch[kScrHist].as<uint32_t>(), ctx->scratch[kScrScan].as<uint32_t>()};

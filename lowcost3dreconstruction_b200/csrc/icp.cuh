@@ -58,11 +58,6 @@ struct IcpConfig {
   int dump_iteration;
   int mode;
   SearchStats* stats;  // per-iteration search statistics (LC3D_STATS=1) or null
-  // icp2.cuh: search-ball policy of the triangle-inequality kernel
-  float r_cap;     // sqrt(gate_ext) rounded up: no search reaches farther (+inf without a gate)
-  float mu0;       // runner-up margin of iteration 0 (the first motion is large: 0)
-  float mu_min, mu_max, mu_kappa;  // later: margin = clamp(kappa * last motion of the point, min, max)
-  float tab_wmax;  // widest ball (cells) served by the row-offset table
 };
 
 __global__ void icp_state_init(IcpState* st) {
@@ -233,40 +228,108 @@ __device__ __forceinline__ bool solve6_dev(double (&A)[36], double (&b)[6], doub
   return true;
 }
 
-// Estimator + pose composition + DefaultConvergenceCriteria; run by
-// one thread of the last block.  v = the NV reduced sums.
+// The same elimination spread over the lanes of one warp: lane r < 6 owns row r of [A | b].
+// Per column the pivot is the unused row with the largest |entry| (butterfly arg-max over the
+// lanes), its row is broadcast, every other unused row eliminates in parallel; the back
+// substitution walks the pivots in reverse.  Each row sees exactly the operations of the
+// single-thread version above (same pivots, same order), so the results are identical; the
+// dependent chain shrinks from ~600 to ~100 fp64 operations.  All 32 lanes must call; v = the
+// reduced sums (upper triangle packed, then the right-hand side).  Returns false if singular.
+__device__ __forceinline__ bool solve6_warp(const double* __restrict__ v, double (&x)[6]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int r = lane < 6 ? lane : 0;
+  double a[6], b;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int i = r < k ? r : k, j = r < k ? k : r;  // symmetric fill from the packed upper triangle
+    a[k] = v[i * 6 - (i * (i - 1)) / 2 + (j - i)];
+  }
+  b = v[21 + r];
+  bool used = lane >= 6;  // lanes beyond the matrix never compete for a pivot
+  bool ok = true;
+  int prow[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    // arg-max of |a[c]| over the unused rows; ties -> lower lane
+    double best = used ? -1.0 : fabs(a[c]);
+    int who = lane;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(full, best, o);
+      const int ow = __shfl_xor_sync(full, who, o);
+      if (ob > best || (ob == best && ow < who)) {
+        best = ob;
+        who = ow;
+      }
+    }
+    who = __shfl_sync(full, who, 0);  // lanes 0..7 agree; take lane 0's view
+    prow[c] = who;
+    double piv[6], pb;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) piv[k] = __shfl_sync(full, a[k], who);
+    pb = __shfl_sync(full, b, who);
+    ok = ok && piv[c] != 0.0;
+    const double pc = ok ? piv[c] : 1.0;
+    if (lane == who) used = true;
+    if (!used) {
+      const double f = a[c] / pc;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k >= c) a[k] -= f * piv[k];
+      b -= f * pb;
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 6; ++cc) {
+    const int c = 5 - cc;
+    double s = b;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k > c) s -= a[k] * x[k];
+    const double xc = s / a[c];
+    x[c] = __shfl_sync(full, xc, prow[c]);
+  }
+  return ok;
+}
+
+// Estimator + pose composition + DefaultConvergenceCriteria; run by ONE
+// WARP of the last block (all 32 lanes call).  The 6x6 solve is spread over the lanes, the three
+// sincos run on three lanes, lane L < 16 composes entry L of final_transformation_; the scalar
+// bookkeeping is evaluated redundantly and written by lane 0.  v = the NV reduced sums.
 template <int MODE>
 __device__ void icp_solve_and_test(IcpState* st, const IcpConfig& cfg, const double* v) {
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const double cnt = v[NV - 1];
-  st->last_corr = (long long)cnt;
-  st->last_mse = cnt > 0 ? v[NV - 2] / cnt : 0.0;
+  const double mse = cnt > 0 ? v[NV - 2] / cnt : 0.0;
+  // everything read from the state up front (lane 0 overwrites it below)
+  const int iter = st->iter + 1;
+  const double prev_mse = st->prev_mse;
+  const float Fin = lane < 16 ? st->Tfinal[lane] : 0.0f;
   if (cnt < 3.0) {  // "Not enough correspondences found"
-    st->state = LC3D_STATE_NO_CORRESPONDENCES;
-    st->converged = 0;
-    st->done = 1;
+    if (lane == 0) {
+      st->last_corr = (long long)cnt;
+      st->last_mse = mse;
+      st->state = LC3D_STATE_NO_CORRESPONDENCES;
+      st->converged = 0;
+      st->done = 1;
+    }
     return;
   }
   float T[16];
+#pragma unroll
   for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
   if (MODE == LC3D_ICP_POINT_TO_PLANE) {
-    double A[36], b[6], x[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i; j < 6; ++j) {
-        const int k = i * 6 - (i * (i - 1)) / 2 + (j - i);  // upper-triangle packing
-        A[i * 6 + j] = v[k];
-        A[j * 6 + i] = v[k];
-      }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) b[i] = v[21 + i];
-    if (solve6_dev(A, b, x)) {
-      double al = x[0], be = x[1], ga = x[2];
-      double sa, ca, sb, cb, sg, cg;
-      sincos(al, &sa, &ca);
-      sincos(be, &sb, &cb);
-      sincos(ga, &sg, &cg);
+    double x[6];
+    if (solve6_warp(v, x)) {
+      // lane 0,1,2: sincos of alpha, beta, gamma
+      double sn = 0.0, cs = 1.0;
+      if (lane < 3) sincos(x[lane], &sn, &cs);
+      const double sa = __shfl_sync(full, sn, 0), ca = __shfl_sync(full, cs, 0);
+      const double sb = __shfl_sync(full, sn, 1), cb = __shfl_sync(full, cs, 1);
+      const double sg = __shfl_sync(full, sn, 2), cg = __shfl_sync(full, cs, 2);
       T[0] = (float)(cg * cb);
       T[1] = (float)(-sg * ca + cg * sb * sa);
       T[2] = (float)(sg * sa + cg * sb * ca);
@@ -295,24 +358,33 @@ __device__ void icp_solve_and_test(IcpState* st, const IcpConfig& cfg, const dou
           (float)(mu_d[i] - (R[i * 3 + 0] * mu_s[0] + R[i * 3 + 1] * mu_s[1] + R[i * 3 + 2] * mu_s[2]));
     }
   }
-  // final_transformation_ = transformation_ * final_transformation_ (Matrix4f, float32)
-  float F[16];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      float s = __fmul_rn(T[i * 4 + 0], st->Tfinal[0 * 4 + j]);
-      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 1], st->Tfinal[1 * 4 + j]));
-      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 2], st->Tfinal[2 * 4 + j]));
-      s = __fadd_rn(s, __fmul_rn(T[i * 4 + 3], st->Tfinal[3 * 4 + j]));
-      F[i * 4 + j] = s;
+  // final_transformation_ = transformation_ * final_transformation_ (Matrix4f, float32):
+  // lane L < 16 computes entry (L / 4, L % 4)
+  {
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // row i of T without dynamic register indexing
+      t0 = i == r ? T[r * 4 + 0] : t0;
+      t1 = i == r ? T[r * 4 + 1] : t1;
+      t2 = i == r ? T[r * 4 + 2] : t2;
+      t3 = i == r ? T[r * 4 + 3] : t3;
     }
-  for (int i = 0; i < 16; ++i) {
-    st->T[i] = T[i];
-    st->Tfinal[i] = F[i];
+    float s = __fmul_rn(t0, __shfl_sync(full, Fin, 0 * 4 + j));
+    s = __fadd_rn(s, __fmul_rn(t1, __shfl_sync(full, Fin, 1 * 4 + j)));
+    s = __fadd_rn(s, __fmul_rn(t2, __shfl_sync(full, Fin, 2 * 4 + j)));
+    s = __fadd_rn(s, __fmul_rn(t3, __shfl_sync(full, Fin, 3 * 4 + j)));
+    if (lane < 16) {
+      float tl = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tl = lane == k ? T[k] : tl;
+      st->T[lane] = tl;
+      st->Tfinal[lane] = s;
+    }
   }
-  const int iter = st->iter + 1;
-  st->iter = iter;
   // DefaultConvergenceCriteria::hasConverged
   int state = LC3D_STATE_NOT_CONVERGED;
+  bool keep_mse = false;
   if (iter >= cfg.max_iterations) {
     state = LC3D_STATE_ITERATIONS;
   } else {
@@ -323,19 +395,24 @@ __device__ void icp_solve_and_test(IcpState* st, const IcpConfig& cfg, const dou
     if (cos_angle >= cfg.rot_thr && tsq <= cfg.transl_thr) {
       state = LC3D_STATE_TRANSFORM;
     } else {
-      double mse = st->last_mse;
-      if (fabs(mse - st->prev_mse) < cfg.abs_mse)
+      if (fabs(mse - prev_mse) < cfg.abs_mse)
         state = LC3D_STATE_ABS_MSE;
-      else if (fabs(mse - st->prev_mse) / st->prev_mse < cfg.rel_mse)
+      else if (fabs(mse - prev_mse) / prev_mse < cfg.rel_mse)
         state = LC3D_STATE_REL_MSE;
       else
-        st->prev_mse = mse;
+        keep_mse = true;
     }
   }
-  st->state = state;
-  if (state != LC3D_STATE_NOT_CONVERGED) {
-    st->converged = 1;
-    st->done = 1;
+  if (lane == 0) {
+    st->last_corr = (long long)cnt;
+    st->last_mse = mse;
+    st->iter = iter;
+    if (keep_mse) st->prev_mse = mse;
+    st->state = state;
+    if (state != LC3D_STATE_NOT_CONVERGED) {
+      st->converged = 1;
+      st->done = 1;
+    }
   }
 }
 
@@ -438,10 +515,13 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
   __shared__ float sT[16];
   __shared__ int s_flags[2];
+  __shared__ double s_rows[kIcpThreads / 32][32];
+  __shared__ unsigned s_arrived;
   pdl_wait();  // the previous solve kernel's pose / done flag
   if (threadIdx.x == 0) {
     s_flags[0] = st->done;
     s_flags[1] = st->iter;
+    s_arrived = 0u;
   }
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
   __syncthreads();
@@ -484,6 +564,20 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
         bnd = -slack;
       }
     }
+#ifndef LC3D_NO_OCC_REJECT
+    if (active && !skip && seed_j < 0 && g.occ) {
+      // no previous match: the dilated occupancy of the index may prove that nothing lies
+      // within the gate (non-overlap regions of the first iterations) without any search
+      const QueryCell qc = query_cell(g, q.x, q.y, q.z);
+      if (occ_proves_empty(g, qc.ix, qc.iy, qc.iz)) {
+        const float slack = ((float)g.occ_r - 0.01f) * g.c - cfg.gate_dist;
+        if (slack > cfg.slack_floor) {
+          skip = true;
+          bnd = -slack;
+        }
+      }
+    }
+#endif
     const Best b = nn_search_seeded(g, active && !skip, q.x, q.y, q.z, cfg.gate_ext, seed_j, stats);
     const bool found = active && !skip && b.j >= 0;
     const bool has = found && b.d2 <= cfg.gate;
@@ -536,11 +630,24 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
       }
     }
   }
-  // ---- one partial row per WARP (value-major), no block-level epilogue: warps retire
-  // independently, so small blocks are cheap and the hardware scheduler balances the load
-  const int warp_global = blockIdx.x * (kIcpThreads / 32) + w;
-  const int nwarps = gridDim.x * (kIcpThreads / 32);
-  if (lane < NV) partials[(size_t)lane * nwarps + warp_global] = acc;
+  // ---- one partial row per BLOCK (value-major) without a block barrier: every warp parks its
+  // row in shared memory and retires; the LAST warp to arrive (shared-memory ticket) adds the
+  // rows in warp order (fixed order: deterministic) and writes the block's row.  Warps still
+  // retire independently, and the solve kernel reads 4x fewer rows.
+  s_rows[w][lane] = acc;
+  __threadfence_block();
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&s_arrived, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
+    __threadfence_block();
+    if (lane < NV) {
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += ((volatile double*)s_rows[ww])[lane];
+      partials[(size_t)lane * gridDim.x + blockIdx.x] = s;
+    }
+  }
 }
 
 // Second kernel of an iteration: block v reduces estimator value v over all warp rows in a
@@ -590,12 +697,13 @@ __global__ void __launch_bounds__(kSolveThreads)
   }
   __syncthreads();
   if (s_ticket != (unsigned)(NV - 1)) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // one warp solves (icp_solve_and_test is warp-collective)
     __threadfence();
+    const double mine = threadIdx.x < NV ? __ldcg(reduced + threadIdx.x) : 0.0;
     double red[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) red[k] = __ldcg(reduced + k);
-    st->ticket = 0;
+    for (int k = 0; k < NV; ++k) red[k] = __shfl_sync(0xffffffffu, mine, k);
+    if (threadIdx.x == 0) st->ticket = 0;
     icp_solve_and_test<MODE>(st, cfg, red);
   }
 }

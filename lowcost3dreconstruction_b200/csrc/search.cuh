@@ -349,6 +349,16 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
 #ifndef LC3D_DEFER_W
 #define LC3D_DEFER_W 2
 #endif
+#ifndef LC3D_COOP_W
+#define LC3D_COOP_W 2
+#endif
+#ifndef LC3D_COOP_LANES
+#define LC3D_COOP_LANES 0
+#endif
+constexpr int kCoopW = LC3D_COOP_W;          // balls wider than this many cells count as wide
+// at most this many wide lanes per warp go cooperative.  0 = off, the measured optimum on the bench
+// pair (same-box A/B, profiles/r02_summary.md: 0 -> 0.73 ms loop, 3 -> 0.75, 6 -> 0.80, 12 -> 0.90)
+constexpr int kCoopLanes = LC3D_COOP_LANES;
 constexpr int kDeferW = LC3D_DEFER_W;
 template <bool DEFER = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, float qx, float qy,
@@ -398,7 +408,17 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
   const bool borrowed = need && !seeded && !probed && b.j >= 0;
   // 4. ball walk for every lane whose ball is small enough, warp-cooperative rings otherwise
   const int Wl = need ? ball_halfwidth(g, b.d2) : 0;
-  const bool walk = need && Wl <= (DEFER ? kDeferW : kBallMaxW);
+  // A FEW lanes with wide balls would drag the whole warp through their windows in lockstep
+  // (thousands of instructions at 1/32 utilisation): when there are at most kCoopLanes of them
+  // they are left out of the per-lane walk and handled one at a time by all 32 lanes below.
+  // Many wide lanes (incoherent early iterations, non-overlap regions) stay in the per-lane
+  // walk, where they keep each other company.
+  int wmax = DEFER ? kDeferW : kBallMaxW;
+  if (!DEFER && kCoopLanes > 0) {
+    const unsigned wide = __ballot_sync(full, need && Wl > kCoopW && b.j >= 0);
+    if (wide && __popc(wide) <= kCoopLanes) wmax = kCoopW;
+  }
+  const bool walk = need && (Wl <= wmax || (b.j < 0 && Wl <= kBallMaxW));
   unsigned n_cand = 0, n_rows = 0;
   if (__any_sync(full, walk))
     ball_walk(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
@@ -439,7 +459,7 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
     const float wx = __shfl_sync(full, qx, src);
     const float wy = __shfl_sync(full, qy, src);
     const float wz = __shfl_sync(full, qz, src);
-    nn_phase2_warp(g, wx, wy, wz, wb);
+    if (!nn_ball_warp(g, wx, wy, wz, wb)) nn_phase2_warp(g, wx, wy, wz, wb);
     if (lane == src) b = wb;
     if (wb.j >= 0) last_j = wb.j;
   }

@@ -35,9 +35,15 @@
 
 namespace lc3d {
 
-constexpr int kI3Threads = 256;
+#ifndef LC3D_I3_THREADS
+#define LC3D_I3_THREADS 256
+#endif
+constexpr int kI3Threads = LC3D_I3_THREADS;
 constexpr int kI3Warps = kI3Threads / 32;
-constexpr int kListK = 16;  // candidate-list capacity per source point
+#ifndef LC3D_LIST_K
+#define LC3D_LIST_K 8
+#endif
+constexpr int kListK = LC3D_LIST_K;  // candidate-list capacity per source point
 
 #ifndef LC3D_I3_MINBLOCKS
 #define LC3D_I3_MINBLOCKS 4
@@ -203,10 +209,19 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
     if (need) {
       nl = (lists.cnt && iter > 0) ? (int)lists.cnt[i] : 0;
       if (nl > 0) {
-        // cached candidates: every target point within Lb of the point is among them
-        for (int k = 0; k < nl; ++k) {
-          const int j = lists.lst[(size_t)k * n + i];
-          consider(__ldg(&g.pts[j]), j, q.x, q.y, q.z, b);
+        // cached candidates: every target point within Lb of the point is among them.  Loads are
+        // issued in batches of 8 (indices, then points) so that a list costs two memory round
+        // trips per batch instead of two per entry.
+        for (int k0 = 0; k0 < nl; k0 += 8) {
+          int jj[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) jj[k] = k0 + k < nl ? lists.lst[(size_t)(k0 + k) * n + i] : -1;
+          float4 pp[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pp[k] = jj[k] >= 0 ? __ldg(&g.pts[jj[k]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (jj[k] >= 0) consider(pp[k], jj[k], q.x, q.y, q.z, b);
         }
         if (b.j >= 0 && sqrtf(b.d2) * 1.00002f < Lb) need = false;  // exact nearest neighbour
       } else if (mj >= 0) {
@@ -215,13 +230,22 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
         need = false;  // still nothing within the gate
       }
     }
+    float Lkeep = Lb;
+    if (need && b.j < 0) {
+      // no candidate at all: the dilated occupancy may prove that nothing lies within the gate
+      const QueryCell qc = query_cell(g, q.x, q.y, q.z);
+      if (occ_proves_empty(g, qc.ix, qc.iy, qc.iz)) {
+        need = false;
+        Lkeep = ((float)g.occ_r - 0.01f) * g.c;
+      }
+    }
     s_qx[tid] = q.x;
     s_qy[tid] = q.y;
     s_qz[tid] = q.z;
     s_j[tid] = b.j;
     s_d2[tid] = b.d2;
     s_oi[tid] = b.oi;
-    s_L[tid] = need ? 0.0f : Lb;
+    s_L[tid] = need ? 0.0f : Lkeep;
     s_nlst[tid] = (unsigned char)(need ? 0 : nl);
     // list margin: motion still to come is a small multiple of the last motion
     const float mu = cfg.mu_kappa * delta;
@@ -304,7 +328,22 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
     }
     __syncthreads();
     const int S2 = s_n2;
-    // pass 2: the whole ball
+#ifdef LC3D_I3_COOP_PASS2
+    // pass 2, cooperative variant: one WARP per point
+    for (int e = w; e < S2; e += kI3Warps) {
+      const int slot = s_q2[e];
+      float qx, qy, qz;
+      Best b;
+      load_slot(slot, qx, qy, qz, b);
+      if (!nn_ball_warp(g, qx, qy, qz, b)) nn_phase2_warp(g, qx, qy, qz, b);
+      if (lane == 0) resolve(slot, b);
+      if (lane == 0 && b.j >= 0 && s_mu[slot] >= 0.0f) s_ql[atomicAdd(&s_nl, 1)] = (unsigned short)slot;
+    }
+    const int S3 = 0;
+    __syncthreads();
+#else
+    // pass 2: every row of the ball (neighbouring points have similar balls, so the lanes of a
+    // warp stay roughly in step); balls wider than the row table go to the ring search
     if (w * 32 < S2) {
       const bool act = tid < S2;
       const int slot = act ? s_q2[tid] : 0;
@@ -312,12 +351,8 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
       Best b;
       load_slot(slot, qx, qy, qz, b);
       const float Rc = sqrtf(b.d2) * g.inv_c * 1.0001f + 0.01f;  // ball radius in cells
-      bool walk = act && Rc <= cfg.tab_wmax;
+      const bool walk = act && Rc <= cfg.tab_wmax;
       bool ok = false;
-      if (walk && b.j < 0 && coarse_ball_empty_thread(g, qx, qy, qz, Rc)) {
-        walk = false;  // nothing in reach at all
-        ok = true;
-      }
       if (__any_sync(full, walk)) {
         const bool okw = walk_rows<false>(g, rowtab, walk, qx, qy, qz, kTabN, 1 << 20, b, 0.f, nullptr, 0, nullptr,
                                           nullptr, STATS ? &n_rows : nullptr, STATS ? &n_cand : nullptr);
@@ -330,7 +365,6 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
       push(act && ok && b.j >= 0 && s_mu[slot] >= 0.0f, s_ql, &s_nl, slot);
     }
     __syncthreads();
-    // rare: balls wider than the row table (huge gates, no gate): warp-cooperative ring search
     const int S3 = s_n3;
     for (int e = w; e < S3; e += kI3Warps) {
       const int slot = s_q3[e];
@@ -340,6 +374,7 @@ __global__ void __launch_bounds__(kI3Threads, LC3D_I3_MINBLOCKS)
       nn_phase2_warp(g, qx, qy, qz, b);
       if (lane == 0) resolve(slot, b);
     }
+#endif
     // candidate lists of the points resolved above (those with a motion small enough to pay)
     const int SL = s_nl;
     if (lists.cnt && w * 32 < SL) {
