@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — ICP iterations/s of the fine-registration hot path (BASELINE.json metric).
+"""bench.py — ICP iterations/s of the fine-registration hot path (BASELINE.json metric), plus the
+36-view chain pairs/s of the same metric string in `extra.chain`.
 
 Workload (configs[1]): point-to-plane ICP (max_corr 0.02 m, 50-iteration cap, PCL convergence
 criteria) of a ~307k x ~307k synthetic Kinect-v1 pair 5 degrees apart on the turntable, target
 normals from our k=30 normal-estimation pass.  A *step* is one complete pair alignment on
 device-resident clouds: spatial-index build over the target + the whole ICP loop +
 getFitnessScore.  value = ICP iterations executed / time, summed over steps (index build and
-fitness are therefore amortised INTO the number, not excluded).  At N GPUs every rank aligns
-its own pair of the view chain (pair r+1 -> r), only the 4x4 results are exchanged (NCCL
-all_gather) and rank 0 composes poses: weak scaling, value = all ranks' iterations / max time.
+fitness are therefore amortised INTO the number, not excluded).  At N GPUs every rank aligns its
+own pair of the view chain (pair r+1 -> r); nothing crosses NVLink inside a step — the per-step
+4x4 records stay on the rank and are gathered ONCE after the timed region (one NCCL all_gather),
+rank 0 composes the poses: weak scaling, value = all ranks' iterations / max time.
+
+`extra.chain` (configs[2]): the 36-view turntable chain — per view VoxelGrid 2 mm + SOR k=50 +
+normals k=30 chained on the device (lc3d_prepare_view), per pair point-to-plane ICP on the
+resident views — sharded over the N ranks in contiguous pair blocks, one gather per chain:
+pairs/s = 35 x repetitions / max-over-ranks wall time (strong scaling: the chain is fixed).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 """
@@ -16,8 +23,8 @@ from __future__ import annotations
 
 import argparse
 import json
+import multiprocessing as mp
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -33,72 +40,114 @@ MAX_ITER = 50
 K_NORMALS = 30
 WORKLOAD = ("point-to-plane ICP, 640x480 synthetic Kinect-v1 full-frame pair (~307k x ~307k pts, 5 deg "
             "turntable step), max_corr=0.02 m, k=30 normals, 50-iteration cap")
+CHAIN_VIEWS = 36
+CHAIN_STEP = 360.0 / CHAIN_VIEWS
+CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL = 0.002, 50, 1.0
+
+
+# ------------------------------------------------------------------------------------ inputs
+
+def _render(job):
+    from lowcost3dreconstruction_b200 import synth
+    view, step, backdrop = job
+    return synth.kinect_view(view, step_deg=step, backdrop=backdrop)
+
+
+def render_views(jobs):
+    """[(view, step_deg, backdrop)] -> clouds; cached under /tmp, rendered in a process pool
+    (numpy ray marching, ~1-2 s per view on one core).  Must run BEFORE CUDA is initialised."""
+    out, todo = {}, []
+    for j in jobs:
+        path = f"/tmp/lc3d_bench_view_{j[0]}_{j[1]}_{j[2]}.npy"
+        if os.path.exists(path):
+            out[j] = np.load(path)
+        else:
+            todo.append(j)
+    if todo:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        procs = max(1, min(len(todo), (os.cpu_count() or 1) // max(world, 1), 16))
+        if procs > 1:
+            with mp.get_context("fork").Pool(procs) as pool:
+                res = pool.map(_render, todo)
+        else:
+            res = [_render(j) for j in todo]
+        for j, c in zip(todo, res):
+            out[j] = c
+            try:
+                np.save(f"/tmp/lc3d_bench_view_{j[0]}_{j[1]}_{j[2]}.npy", c)
+            except OSError:
+                pass
+    return out
 
 
 def load_pair(view: int):
-    """(source = view+1, target = view) clouds, cached under /tmp (rendering takes ~2 s/view)."""
-    from lowcost3dreconstruction_b200 import synth
-    out = []
-    for v in (view + 1, view):
-        path = f"/tmp/lc3d_bench_view_{v}_{STEP_DEG}.npy"
-        if os.path.exists(path):
-            c = np.load(path)
-        else:
-            c = synth.kinect_view(v, step_deg=STEP_DEG, backdrop="full")
-            try:
-                np.save(path, c)
-            except OSError:
-                pass
-        out.append(c)
-    return out[0], out[1]
+    """(source = view+1, target = view) clouds of the bench pair."""
+    v = render_views([(view + 1, STEP_DEG, "full"), (view, STEP_DEG, "full")])
+    return v[(view + 1, STEP_DEG, "full")], v[(view, STEP_DEG, "full")]
+
+
+def host_info() -> dict:
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"host_cores": os.cpu_count(), "cpu_model": model}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons polled through NVML (every ~2 ms) while the timed region runs."""
 
     def __init__(self, gpu: int):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.stop_flag, self.thread, self.h = gpu, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted({nm for _, bits in self.rows for nm, m in names.items() if bits & m})
+        sm = [c for c, _ in self.rows]
         try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                for nm, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            smax = None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": reasons,
+                "samples": len(sm)}
 
+
+# ----------------------------------------------------------------------------- reference arm
 
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU path for this workload.  PCL cannot be built in
@@ -132,14 +181,90 @@ def run_reference(args, rank: int, world: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_source": int(S.n), "n_target": int(T.n), "mode": "point-to-plane",
                    "step": "kd-tree build + ICP loop + fitness on host arrays"},
-        "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} complete alignments of the same pair (kd-tree build + "
-                                   f"{iters // max(args.steps, 1)} iterations + fitness each); oracle restatement of "
-                                   "PCL (PCL itself cannot be built here), 1 thread like pcl::IterativeClosestPoint"},
+        "cpu_baseline": dict({"value": val, "unit": "iterations/s", "cores": 1, "kind": "port",
+                              "sample": f"{args.steps} complete alignments of the same pair (kd-tree build + "
+                                        f"{iters // max(args.steps, 1)} iterations + fitness each); oracle restatement "
+                                        "of PCL (PCL itself cannot be built here), 1 thread like "
+                                        "pcl::IterativeClosestPoint"}, **host_info()),
         "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
+
+# -------------------------------------------------------------------------------- chain arm
+
+def chain_inputs(rank: int, world: int):
+    """Host-side inputs of this rank's block of the 36-view chain: raw clouds pre-aligned with the
+    turntable prior of rotate_align (rotate_align.cpp:224-235) perturbed by a residual error."""
+    from lowcost3dreconstruction_b200 import chain, synth
+    pairs = chain.shard_pairs(CHAIN_VIEWS - 1, world, rank)
+    needed = sorted({p for p in pairs} | {p - 1 for p in pairs})
+    rng = np.random.default_rng(7)
+    resid = {v: synth.rigid(*(rng.normal(0, 0.4, 3)), rng.normal(0, 0.002, 3)) for v in range(CHAIN_VIEWS)}
+    clouds = render_views([(v, CHAIN_STEP, "none") for v in needed])
+    raw = {v: synth.apply_transform(resid[v] @ synth.turntable_prior(v, CHAIN_STEP), clouds[(v, CHAIN_STEP, "none")])
+           for v in needed}
+    return pairs, raw, resid
+
+
+def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | None:
+    import torch
+    import torch.distributed as dist
+    from lowcost3dreconstruction_b200 import api, chain
+
+    def one_chain():
+        """this rank's views prepared on the device (each once), its pairs aligned resident"""
+        prepared, local, npts = {}, np.zeros((CHAIN_VIEWS - 1, chain.RECORD)), []
+
+        def view(v):
+            if v not in prepared:
+                prepared[v], cnt = api.prepare_view(raw[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=ctx)
+                npts.append(cnt[2])
+            return prepared[v]
+
+        for p in pairs:
+            r = api.icp_align(view(p), view(p - 1), MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=ctx)
+            local[p - 1] = chain.pack_record(r)
+            prepared.pop(p - 1).free()
+        for d in prepared.values():
+            d.free()
+        return chain.exchange_records(local, dev), npts  # one gather per chain (20 doubles per pair)
+
+    one_chain()  # warm-up: allocations, NCCL communicator
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rec, npts = one_chain()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    dt = float(tt[0])
+    res = [chain.unpack_record(r) for r in rec]
+    poses = chain.compose_chain([p["transformation"] for p in res])
+    errs = []
+    for p, pr in enumerate(res, start=1):  # ground truth: pair p's residual motion is resid[p-1] . resid[p]^-1
+        Tt = resid[p - 1] @ np.linalg.inv(resid[p])
+        R = pr["transformation"][:3, :3].astype(np.float64) @ Tt[:3, :3].T
+        errs.append(float(np.degrees(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))))
+    return {"pairs_per_sec": (CHAIN_VIEWS - 1) * reps / dt, "unit": "pairs/s", "scaling": "strong", "views": CHAIN_VIEWS,
+            "pairs": CHAIN_VIEWS - 1, "repetitions": reps, "seconds_per_chain": dt / reps,
+            "iterations_total": int(sum(p["iterations"] for p in res)),
+            "converged_pairs": int(sum(p["converged"] for p in res)),
+            "median_rot_err_deg_vs_truth": float(np.median(errs)), "max_rot_err_deg_vs_truth": float(np.max(errs)),
+            "points_per_view_after_voxel_sor": int(np.mean(npts)) if npts else 0,
+            "pose_35_translation_m": [float(x) for x in poses[-1][:3, 3]],
+            "timed": "per view VoxelGrid 2 mm + SOR k=50 + normals k=30 on the device (lc3d_prepare_view, host xyz in), "
+                     "per pair point-to-plane ICP on the resident views, one record gather per chain; wall clock "
+                     "bracketed by barrier + cuda synchronize, max over ranks"}
+
+
+# ---------------------------------------------------------------------------------- main arm
 
 def main():
     ap = argparse.ArgumentParser()
@@ -148,6 +273,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chain", action="store_true")
+    ap.add_argument("--chain-reps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -158,6 +285,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # ---- inputs are rendered before CUDA comes up (fork-based process pool) --------------------
+    src, tgt = load_pair(rank)
+    chain_in = None if args.no_chain else chain_inputs(rank, world)
+
     import torch
     import torch.distributed as dist
     from lowcost3dreconstruction_b200 import api
@@ -167,11 +298,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
-    ctx = api.Context(local_rank, stream=stream.cuda_stream)  # our kernels run on torch's stream
+    # one explicit stream for everything that is timed: our kernels, the L2 flush and the events
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local_rank, stream=stream.cuda_stream)
 
     # ---- this rank's pair of the view chain: view rank+1 -> view rank ----------------------
-    src, tgt = load_pair(rank)
     n_t, c_t = api.normals(tgt, K_NORMALS, ctx=ctx)
     n_s, c_s = api.normals(src, K_NORMALS, ctx=ctx)
     t0 = time.perf_counter()
@@ -185,44 +316,35 @@ def main():
     S = HostCloud(src, normal=n_s, curvature=c_s)
     T = HostCloud(tgt, normal=n_t, curvature=c_t)
     dS, dT = ctx.upload(S), ctx.upload(T)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    rec = torch.zeros(world, 20, dtype=torch.float32, device=dev)
-    mine = torch.zeros(20, dtype=torch.float32, device=dev)
+    with torch.cuda.stream(stream):
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def one_step():
-        r = api.icp_align(dS, dT, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, compute_fitness=True, ctx=ctx)
-        if world > 1:  # only 4x4 matrices (+score, iterations) cross NVLink; rank 0 composes poses
-            mine[:16] = torch.from_numpy(r["transformation"].reshape(16)).to(dev, non_blocking=True)
-            mine[16], mine[17] = float(r["fitness"]), float(r["iterations"])
-            dist.all_gather_into_tensor(rec.view(-1), mine)
-            if rank == 0:
-                G = np.eye(4)
-                for Tm in rec[:, :16].cpu().numpy().reshape(world, 4, 4):
-                    G = G @ Tm.astype(np.float64)
-        return r
+        return api.icp_align(dS, dT, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, compute_fitness=True, ctx=ctx)
 
-    for _ in range(args.warmup):
-        flush.zero_()
-        one_step()
-    # ---- timed region: exactly K steps, device-timed, L2 flushed between steps --------------
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = ctx.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    results = []
-    wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()
-        a.record(stream)
-        results.append(one_step())
-        b.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
+    sampler.start()  # covers warm-up + timed region (the timed region alone lasts ~20 ms)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            one_step()
+        # ---- timed region: exactly K steps, device-timed, L2 flushed between steps ----------
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        results = []
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            results.append(one_step())
+            b.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - wall0
     launches = ctx.launch_count - l0
     clocks = sampler.stop()
     ms_steps = sum(a.elapsed_time(b) for a, b in ev)
@@ -232,56 +354,128 @@ def main():
     ms_fit = sum(r["ms"]["fitness"] for r in results)
     t = torch.tensor([ms_steps, float(iters), ms_loop], dtype=torch.float64, device=dev)
     tmax, tsum = t.clone(), t.clone()
+    gather_ms = 0.0
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        # the one exchange of the run: every step's 4x4 (+ fitness, iterations) from every rank;
+        # rank 0 composes the poses of the `world` chained views
+        mine = torch.tensor(np.stack([np.concatenate([r["transformation"].reshape(16).astype(np.float64),
+                                                      [r["fitness"], r["iterations"], 0.0, 0.0]]) for r in results]),
+                            device=dev)
+        allrec = torch.empty(world, *mine.shape, dtype=mine.dtype, device=dev)
+        torch.cuda.synchronize()
+        g0 = time.perf_counter()
+        dist.all_gather_into_tensor(allrec.view(-1), mine.view(-1))
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        if rank == 0:
+            G = np.eye(4)
+            for Tm in allrec[:, -1, :16].cpu().numpy().reshape(world, 4, 4):
+                G = G @ Tm
     ms_max = float(tmax[0])
     total_iters = float(tsum[1])
     value = total_iters / (ms_max * 1e-3)
 
-    # ---- e2e: the reference-facing host-buffer C-ABI call, pinned host memory ----------------
+    # ---- e2e: the reference-facing host-buffer C-ABI call --------------------------------------
+    def reduce_e2e(e_t, e_iters):
+        e = torch.tensor([e_t, float(e_iters)], dtype=torch.float64, device=dev)
+        emax, esum = e.clone(), e.clone()
+        if world > 1:
+            dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+        return float(esum[1]) / float(emax[0])
+
+    def time_e2e(Sx, Tx, reg_out, reps):
+        for _ in range(2):
+            api.icp_align(Sx, Tx, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
+        e_iters, e_t = 0, 0.0
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = api.icp_align(Sx, Tx, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
+            e_t += time.perf_counter() - t0
+            e_iters += r["iterations"]
+        return reduce_e2e(e_t, e_iters)
+
     def pinned(a):
         t_ = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t_, t_.numpy()
+    chain_res = None
+    if chain_in is not None and os.environ.get("LC3D_BENCH_CHAIN_FIRST"):
+        chain_res = run_chain(ctx, rank, world, dev, *chain_in, reps=max(1, args.chain_reps))
+        chain_in = None
+    e_reps = max(3, min(args.steps, 10))
+    # (a) headline: packed arrays in pinned host memory (what a caller that owns its buffers does)
     keep = [pinned(x) for x in (src, n_s, tgt, n_t, np.empty_like(src), np.empty_like(src))]
     Sp = HostCloud(keep[0][1], normal=keep[1][1])
     Tp = HostCloud(keep[2][1], normal=keep[3][1])
-    reg_out = (keep[4][1], keep[5][1])  # pinned result buffers: registered xyz + normals
-    for _ in range(2):
-        api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
-    e_iters, e_t = 0, 0.0
-    for _ in range(max(3, min(args.steps, 10))):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r = api.icp_align(Sp, Tp, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
-        e_t += time.perf_counter() - t0
-        e_iters += r["iterations"]
-    e = torch.tensor([e_t, float(e_iters)], dtype=torch.float64, device=dev)
-    emax, esum = e.clone(), e.clone()
-    if world > 1:
-        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(esum, op=dist.ReduceOp.SUM)
-    e2e_val = float(esum[1]) / float(emax[0])
+    e2e_val = time_e2e(Sp, Tp, (keep[4][1], keep[5][1]), e_reps)
     h2d = int(Sp.n * 24 + Tp.n * 24)
     d2h = int(Sp.n * 24 + 128)
+    # (b) what INTEGRATION.md's in-main() binding passes: PCL's own 48-byte PointXYZRGBNormal array in
+    # pageable memory (std::vector), registered cloud back into pageable memory
+    def aos(xyz, nrm, curv):
+        a = np.zeros((len(xyz), 12), dtype=np.float32)
+        a[:, 0:3], a[:, 3], a[:, 4:7], a[:, 9] = xyz, 1.0, nrm, curv
+        return a
+    Sa, Ta = HostCloud.from_pcl_aos(aos(src, n_s, c_s)), HostCloud.from_pcl_aos(aos(tgt, n_t, c_t))
+    e2e_aos = time_e2e(Sa, Ta, (np.empty_like(src), np.empty_like(src)), e_reps)
+
+    # ---- 36-view chain (configs[2]) -----------------------------------------------------------
+    if chain_in is not None:
+        chain_res = run_chain(ctx, rank, world, dev, *chain_in, reps=max(1, args.chain_reps))
+
+    # ---- configs[0]: the reference's own mode — point-to-point, ~200k-point pair, 50 iterations ----
+    cfg1 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        v1 = render_views([(1, STEP_DEG, "panel"), (0, STEP_DEG, "panel")])
+        s1, t1 = v1[(1, STEP_DEG, "panel")], v1[(0, STEP_DEG, "panel")]
+        d1s, d1t = ctx.upload(HostCloud(s1)), ctx.upload(HostCloud(t1))
+        for _ in range(2):
+            g1 = api.icp_align(d1s, d1t, MAX_CORR, MAX_ITER, mode=api.POINT_TO_POINT, ctx=ctx)
+        reps1, ms1 = 5, 0.0
+        for _ in range(reps1):
+            g1 = api.icp_align(d1s, d1t, MAX_CORR, MAX_ITER, mode=api.POINT_TO_POINT, ctx=ctx)
+            ms1 += g1["ms"]["total"]
+        t0 = time.perf_counter()
+        o1 = orc.icp_align(s1, t1, MAX_CORR, MAX_ITER, mode=0)
+        dt1 = time.perf_counter() - t0
+        o1f = orc.icp_align(s1, t1, MAX_CORR, MAX_ITER, mode=0, umeyama_f32=True)  # PCL's float32 Umeyama sums
+
+        def delta(o):
+            return {"iterations": int(o["iterations"]), "state": int(o["state"]),
+                    "transform_max_abs_diff_vs_gpu": float(np.abs(o["transformation"] - g1["transformation"]).max()),
+                    "fitness_rel_diff_vs_gpu": float(abs(o["fitness"] - g1["fitness"]) / o["fitness"])}
+        cfg1 = {"workload": "point-to-point ICP (pcl_tools/fine_registration.cpp:105), synthetic Kinect-v1 pair with "
+                            "finite backdrop, 5 deg step, max_corr 0.02 m, 50-iteration cap",
+                "n_source": int(len(s1)), "n_target": int(len(t1)), "gpu_iterations": int(g1["iterations"]),
+                "gpu_state": int(g1["state"]), "gpu_iters_per_sec_resident": g1["iterations"] * reps1 / (ms1 * 1e-3),
+                "gpu_ms_per_alignment": ms1 / reps1, "cpu_iters_per_sec": o1["iterations"] / dt1,
+                "oracle_fp64_sums": delta(o1), "oracle_float32_sums_like_pcl": delta(o1f)}
+        d1s.free()
+        d1t.free()
 
     # ---- roofline of the dominant kernel (the fused ICP iteration) ---------------------------
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
+    peaks, prof = {}, {}
+    for name, dst in (("MEASURED_PEAKS.json", peaks), (os.path.join("profiles", "r02_roofline_traffic.json"), prof)):
+        try:
+            with open(os.path.join(ROOT, name)) as f:
+                dst.update(json.load(f))
+        except (OSError, ValueError):
+            pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_iter_s = (ms_loop / max(iters, 1)) * 1e-3
     alg_bytes = 64.0 * S.n  # whole point-to-plane iteration = 64 B per source point
     achieved = alg_bytes / t_iter_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read+write per launch of a converged iteration from
-                # profiles/r01c_icp_kernels_ncu_full.csv (ncu --set full, caches flushed per replay):
-                # 17.7 MB <= the algorithmic bytes, i.e. no DRAM re-reads (live, the set is L2-resident)
-                "traffic": 17.7e6, "kernel": "icp_iteration_kernel<point-to-plane>",
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of a converged iteration, from the
+                # committed `ncu --set full` capture named in that file (caches flushed per replay)
+                "traffic": prof.get("dram_bytes_per_launch"), "traffic_source": prof.get("source"),
+                "kernel": "icp_iteration_kernel<point-to-plane> (+ icp_solve_kernel)",
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_iter_s * 1e6,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"}
 
@@ -292,26 +486,37 @@ def main():
             t0 = time.perf_counter()
             o = orc.icp_align(S, T, MAX_CORR, MAX_ITER, mode=1, compute_fitness=True)
             dt = time.perf_counter() - t0
-            cpu = {"value": o["iterations"] / dt, "unit": "iterations/s", "cores": 1, "kind": "port",
-                   "sample": f"one full alignment of the same pair (kd-tree build + {o['iterations']} iterations + "
-                             f"fitness) = {dt:.1f} s; oracle restatement of PCL, 1 thread",
-                   "iterations": o["iterations"],
-                   "transform_max_abs_diff_vs_gpu": float(np.abs(o["transformation"] - results[-1]["transformation"]).max())}
+            g = results[-1]
+            cpu = dict({"value": o["iterations"] / dt, "unit": "iterations/s", "cores": 1, "kind": "port",
+                        "sample": f"one full alignment of the same pair (kd-tree build + {o['iterations']} iterations "
+                                  f"+ fitness) = {dt:.1f} s; oracle restatement of PCL, 1 thread",
+                        "iterations": o["iterations"],
+                        "transform_max_abs_diff_vs_gpu": float(np.abs(o["transformation"] - g["transformation"]).max()),
+                        "fitness_rel_diff_vs_gpu": float(abs(o["fitness"] - g["fitness"]) / o["fitness"])},
+                       **host_info())
+            cpu["cfg1_point_to_point"] = cfg1
         line = {
             "metric": "icp_iters_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_source": int(S.n), "n_target": int(T.n), "mode": "point-to-plane",
-                       "pairs_per_gpu": 1, "l2": "flushed between steps (256 MiB write)",
+                       "pairs_per_gpu": 1, "l2": "flushed between steps (256 MiB write on the timed stream)",
                        "step": "index build + ICP loop + fitness on resident clouds"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_memory": "pinned, packed xyz / normal arrays"},
             "gpu_launches": int(launches), "clocks": clocks,
             "extra": {"iterations_per_alignment": iters / args.steps, "pairs_per_sec": world * args.steps / (ms_max * 1e-3),
                       "ms_index_per_step": ms_index / args.steps, "ms_loop_per_step": ms_loop / args.steps,
                       "ms_fitness_per_step": ms_fit / args.steps, "loop_only_iters_per_sec": iters / (ms_loop * 1e-3),
                       "ms_normals_k30_host_call": ms_normals, "wall_s_timed_region": wall,
-                      "fitness": results[-1]["fitness"], "state": results[-1]["state"]},
+                      "fitness": results[-1]["fitness"], "state": results[-1]["state"],
+                      "record_gather_ms_after_timed_region": gather_ms,
+                      "e2e_pcl_aos_pageable": {"value": e2e_aos, "unit": "iterations/s",
+                                               "h2d_bytes_per_step": int(Sa.n * 48 + Ta.n * 48), "d2h_bytes_per_step": d2h,
+                                               "host_memory": "pageable, 48-byte pcl::PointXYZRGBNormal AoS "
+                                                              "(INTEGRATION.md section B binding)"},
+                      "chain": chain_res},
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -207,6 +207,32 @@ int lc3d_euclidean_clusters(lc3d_ctx* ctx, const lc3d_cloud* cloud, double toler
                             int64_t max_size, int32_t* out_labels, int64_t* out_sizes, int64_t sizes_cap,
                             int64_t* out_count);
 
+/* ------------------------------------------------- in-process view pipeline -- */
+
+/* The per-view stages that scripts/alignment.sh:99-100 (outlier_removal, normals) and the
+ * turntable chain of BASELINE configs[2] (VoxelGrid 2 mm + SOR k=50 + normals) run before the
+ * pairwise ICP, chained on the device: no PLY file and no host copy between the stages (SURVEY §8f
+ * rank 3).  Each stage is exactly the computation of its stage-by-stage entry point
+ * (lc3d_voxel_grid / lc3d_sor / lc3d_normals), so the result is bit-identical to calling them
+ * in sequence through host buffers.  A stage is skipped when its parameter is <= 0. */
+typedef struct lc3d_prepare_params {
+  float leaf_size;        /* pcl::VoxelGrid cubic leaf (cloud_downsampling.cpp:74), <= 0: skip          */
+  int32_t sor_mean_k;     /* StatisticalOutlierRemoval meanK (outlier_removal.cpp:81), <= 0: skip      */
+  double sor_stddev_mul;  /* setStddevMulThresh (outlier_removal.cpp:82)                                */
+  int32_t normals_k;      /* NormalEstimation setKSearch (normal_estimation.cpp:96), <= 0: no normals  */
+  float viewpoint[3];     /* setViewPoint (normal_estimation.cpp:98-105)                                */
+} lc3d_prepare_params;
+
+/* xyz of `cloud` in, resident cloud out (xyz, and normals + curvature when normals_k > 0), ready
+ * for lc3d_icp_align_resident.  counts (may be NULL): points after VoxelGrid, after SOR, final. */
+int lc3d_prepare_view(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_prepare_params* params,
+                      lc3d_dcloud** out, int64_t counts[3]);
+
+/* Copies a resident cloud back: out_xyz n x 3; out_normal n x 3 and out_curvature n may be NULL
+ * (they are left untouched when the cloud carries no normals). */
+int lc3d_cloud_download(lc3d_ctx* ctx, const lc3d_dcloud* dc, float* out_xyz, float* out_normal,
+                        float* out_curvature);
+
 /* ------------------------------------------------------------ transform ----- */
 
 /* pcl::transformPointCloudWithNormals (pcl_tools/transform.cpp:84-90; SURVEY §8f

@@ -69,6 +69,17 @@ class IcpOutputs(C.Structure):
     ]
 
 
+class PrepareParams(C.Structure):
+    """struct lc3d_prepare_params."""
+    _fields_ = [
+        ("leaf_size", C.c_float),
+        ("sor_mean_k", C.c_int32),
+        ("sor_stddev_mul", C.c_double),
+        ("normals_k", C.c_int32),
+        ("viewpoint", C.c_float * 3),
+    ]
+
+
 POINT_TO_POINT = 0
 POINT_TO_PLANE = 1
 STATE_NAMES = {0: "NOT_CONVERGED", 1: "ITERATIONS", 2: "TRANSFORM", 3: "ABS_MSE", 4: "REL_MSE",
@@ -82,6 +93,7 @@ SYMBOLS = [
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
     "lc3d_voxel_grid", "lc3d_sor", "lc3d_transform", "lc3d_box_dedup", "lc3d_euclidean_clusters",
+    "lc3d_prepare_view", "lc3d_cloud_download",
 ]
 
 
@@ -176,6 +188,10 @@ def _declare(lib):
     lib.lc3d_euclidean_clusters.restype = C.c_int
     lib.lc3d_transform.argtypes = [vp, cp, C.POINTER(C.c_float), vp, vp]
     lib.lc3d_transform.restype = C.c_int
+    lib.lc3d_prepare_view.argtypes = [vp, cp, C.POINTER(PrepareParams), C.POINTER(vp), C.POINTER(i64)]
+    lib.lc3d_prepare_view.restype = C.c_int
+    lib.lc3d_cloud_download.argtypes = [vp, vp, vp, vp, vp]
+    lib.lc3d_cloud_download.restype = C.c_int
     return lib
 
 

@@ -68,12 +68,24 @@ class Context:
         hc = _hc(cloud)
         h = C.c_void_p()
         self._check(self._lib.lc3d_cloud_upload(self._h, hc.ref(), C.byref(h)), "lc3d_cloud_upload")
-        return DeviceCloud(self, h, hc.n)
+        return DeviceCloud(self, h, hc.n, has_normal=hc.normal is not None)
 
 
 class DeviceCloud:
-    def __init__(self, ctx: Context, handle, n: int):
-        self.ctx, self._h, self.n = ctx, handle, n
+    """A cloud resident in HBM (struct lc3d_dcloud): xyz, optionally normals + curvature."""
+
+    def __init__(self, ctx: Context, handle, n: int, has_normal: bool = False):
+        self.ctx, self._h, self.n, self.has_normal = ctx, handle, n, has_normal
+
+    def download(self):
+        """(xyz (n,3), normal (n,3) or None, curvature (n,) or None) as host arrays."""
+        xyz = np.empty((self.n, 3), dtype=np.float32)
+        nrm = np.empty((self.n, 3), dtype=np.float32) if self.has_normal else None
+        curv = np.empty(self.n, dtype=np.float32) if self.has_normal else None
+        self.ctx._check(self.ctx._lib.lc3d_cloud_download(
+            self.ctx._h, self._h, xyz.ctypes.data, None if nrm is None else nrm.ctypes.data,
+            None if curv is None else curv.ctypes.data), "lc3d_cloud_download")
+        return xyz, nrm, curv
 
     def free(self):
         if self._h and self.ctx._h:
@@ -126,9 +138,12 @@ def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, tran
     o = IcpOutputs()
     out = {}
     resident = isinstance(src, DeviceCloud)
+    if resident != isinstance(tgt, DeviceCloud):
+        raise Lc3dError("icp_align: source and target must both be resident (DeviceCloud) or both host clouds")
     n = src.n if resident else _hc(src).n
     if not resident:
         src, tgt = _hc(src), _hc(tgt)
+    src_has_normal = src.has_normal if resident else src.normal is not None
     if dump_iteration >= 0:
         out["corr_index"] = np.empty(n, dtype=np.int32)
         out["corr_dist2"] = np.empty(n, dtype=np.float32)
@@ -139,14 +154,14 @@ def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, tran
         assert rx.dtype == np.float32 and rx.shape == (n, 3) and rx.flags.c_contiguous
         out["registered_xyz"] = rx
         o.registered_xyz = rx.ctypes.data
-        if rn is not None and (resident or src.normal is not None):
+        if rn is not None and src_has_normal:
             assert rn.dtype == np.float32 and rn.shape == (n, 3) and rn.flags.c_contiguous
             out["registered_normal"] = rn
             o.registered_normal = rn.ctypes.data
     elif want_registered:
         out["registered_xyz"] = np.empty((n, 3), dtype=np.float32)
         o.registered_xyz = out["registered_xyz"].ctypes.data
-        if resident or src.normal is not None:
+        if src_has_normal:
             out["registered_normal"] = np.empty((n, 3), dtype=np.float32)
             o.registered_normal = out["registered_normal"].ctypes.data
     if resident:
@@ -156,6 +171,21 @@ def icp_align(src, tgt, max_correspondence_distance=0.1, max_iterations=50, tran
     ctx._check(rc, "lc3d_icp_align")
     out.update(_result_dict(r))
     return out
+
+
+def prepare_view(cloud, leaf_size: float = 0.0, sor_mean_k: int = 0, sor_stddev_mul: float = 1.0, normals_k: int = 0,
+                 viewpoint=(0.0, 0.0, 0.0), ctx: Context | None = None):
+    """VoxelGrid -> StatisticalOutlierRemoval -> NormalEstimation chained on the device
+    (lc3d_prepare_view): returns (DeviceCloud, (n_after_voxel, n_after_sor, n_final)).  A stage
+    whose parameter is <= 0 is skipped."""
+    ctx = ctx or default_context()
+    c = _hc(cloud)
+    p = _capi.PrepareParams(float(leaf_size), int(sor_mean_k), float(sor_stddev_mul), int(normals_k),
+                            (C.c_float * 3)(*[float(v) for v in viewpoint]))
+    h = C.c_void_p()
+    counts = (C.c_int64 * 3)()
+    ctx._check(ctx._lib.lc3d_prepare_view(ctx._h, c.ref(), C.byref(p), C.byref(h), counts), "lc3d_prepare_view")
+    return DeviceCloud(ctx, h, int(counts[2]), has_normal=normals_k > 0 and counts[2] > 0), tuple(int(x) for x in counts)
 
 
 def nn(cloud, queries=None, max_dist: float = 0.0, ctx: Context | None = None):

@@ -529,6 +529,7 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   for (auto& b : ctx->pinned) b.release();
   ctx->tmp_a.release();
   ctx->tmp_b.release();
+  ctx->pool.release_all();
   if (ctx->grid) {
     ctx->grid->release();
     delete ctx->grid;
@@ -569,6 +570,10 @@ int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out) 
   *out = nullptr;
   lc3d_dcloud* d = new lc3d_dcloud;
   int rc = guarded(ctx, [&] {
+    if (host->n > 0) {
+      d->xyz = ctx->pool.acquire((size_t)host->n * 16);
+      if (host->normal) d->normal = ctx->pool.acquire((size_t)host->n * 16);
+    }
     upload_cloud(ctx, host, d, true);
     LC3D_CUDA(cudaStreamSynchronize(ctx->stream));
   });
@@ -583,8 +588,14 @@ int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out) 
 
 void lc3d_cloud_free(lc3d_ctx* ctx, lc3d_dcloud* dc) {
   if (!dc) return;
-  if (ctx) cudaSetDevice(ctx->device);
-  dc->release();
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    // every use of the cloud was stream-ordered on ctx->stream and the entry points return
+    // synchronised, so the buffers can be handed out again right away
+    dc->park(ctx->pool);
+  } else {
+    dc->release();
+  }
   delete dc;
 }
 

@@ -141,14 +141,65 @@ namespace lc3d {
 struct Grid;
 }
 
+namespace lc3d {
+// Free list of device buffers of resident clouds.  cudaMalloc / cudaFree cost 0.1-5 ms each (and
+// cudaFree synchronises the device; both get slower as the process maps more memory), which would
+// dominate a view chain that uploads and frees a cloud per view: freed cloud buffers are parked
+// here and handed out again, so the steady state of a chain allocates nothing.
+struct BufPool {
+  std::vector<DevBuf> free_list;
+  static constexpr size_t kMaxParked = 32;
+  // a parked buffer of at least `bytes` (and not absurdly larger), or a fresh allocation
+  DevBuf acquire(size_t bytes) {
+    int best = -1;
+    for (int i = 0; i < (int)free_list.size(); ++i)
+      if (free_list[i].cap >= bytes && free_list[i].cap <= 4 * bytes + (1u << 20) &&
+          (best < 0 || free_list[i].cap < free_list[best].cap))
+        best = i;
+    DevBuf b;
+    if (best >= 0) {
+      b = free_list[best];
+      free_list.erase(free_list.begin() + best);
+    } else {
+      b.ensure(bytes);
+    }
+    return b;
+  }
+  void park(DevBuf& b) {
+    if (!b.p) return;
+    if (free_list.size() >= kMaxParked) {  // drop the smallest parked buffer
+      int small = 0;
+      for (int i = 1; i < (int)free_list.size(); ++i)
+        if (free_list[i].cap < free_list[small].cap) small = i;
+      free_list[small].release();
+      free_list.erase(free_list.begin() + small);
+    }
+    free_list.push_back(b);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  void release_all() {
+    for (auto& b : free_list) b.release();
+    free_list.clear();
+  }
+};
+}  // namespace lc3d
+
 struct lc3d_dcloud {
   int64_t n = 0;
   lc3d::DevBuf xyz;     // float4 (x,y,z,1) in input order
-  lc3d::DevBuf normal;  // float4 (nx,ny,nz,0) in input order, or empty
+  lc3d::DevBuf normal;  // float4 (nx,ny,nz,curvature) in input order, or empty
   bool has_normal = false;
   void release() {
     xyz.release();
     normal.release();
+    n = 0;
+    has_normal = false;
+  }
+  // buffers go back to the context's pool instead of cudaFree
+  void park(lc3d::BufPool& pool) {
+    pool.park(xyz);
+    pool.park(normal);
     n = 0;
     has_normal = false;
   }
@@ -173,6 +224,7 @@ struct lc3d_ctx {
   cudaEvent_t ev_aux = nullptr;
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
+  lc3d::BufPool pool;          // parked buffers of freed resident clouds
 };
 
 namespace lc3d {

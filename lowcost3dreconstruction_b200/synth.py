@@ -60,9 +60,14 @@ def _scene_sdf(p: np.ndarray, backdrop: str) -> np.ndarray:
     return f
 
 
+def _rot_x(a: float) -> np.ndarray:
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[1.0, 0.0, 0.0], [0.0, c, -s], [0.0, s, c]])
+
+
 def render_depth(view_angle_rad: float, intr: dict = KINECT_V1, scale: float = 1.0,
                  backdrop: str = "none", seed: int | None = 0, noise: bool = True,
-                 depth_max_mm: float = 2000.0) -> np.ndarray:
+                 depth_max_mm: float = 2000.0, tilt_rad: float = 0.0) -> np.ndarray:
     """Depth image (uint16 mm, 0 = invalid) of the scene rotated by view_angle about +Y
     through the table centre.  backdrop: "none" (object + table), "panel" (finite
     backdrop, ~65 % fill: cfg1) or "full" (every pixel valid: cfg2).  `scale` < 1
@@ -73,7 +78,9 @@ def render_depth(view_angle_rad: float, intr: dict = KINECT_V1, scale: float = 1
     # ray through pixel, parameterised by depth z>0: p = z * d, d = ((j-cx)/fx, -(i-cy)/fy, -1)
     d = np.stack([(jj - cx) / fx, -(ii - cy) / fy, -np.ones_like(jj)], axis=-1).reshape(-1, 3)
     dn = np.linalg.norm(d, axis=-1)
-    rinv = _rot_y(-view_angle_rad)  # world -> scene frame
+    # world -> scene frame; tilt_rad != 0 additionally pitches the scene about X through the table
+    # centre (top / bottom views of scripts/alignment.sh:118-119)
+    rinv = _rot_y(-view_angle_rad) @ _rot_x(-tilt_rad)
     ds = d @ rinv.T
     o = -TABLE_CENTRE_MM @ rinv.T
     z = np.full(d.shape[0], 250.0)
@@ -115,11 +122,32 @@ def backproject(depth_mm: np.ndarray, intr: dict = KINECT_V1, scale: float = 1.0
 
 
 def kinect_view(view: int, step_deg: float = 5.0, scale: float = 1.0, backdrop: str = "none",
-                intr: dict = KINECT_V1, noise: bool = True) -> np.ndarray:
-    """Cloud (n,3) float32, metres, of turntable view `view` (angle = view*step)."""
+                intr: dict = KINECT_V1, noise: bool = True, tilt_deg: float = 0.0) -> np.ndarray:
+    """Cloud (n,3) float32, metres, of turntable view `view` (angle = view*step); tilt_deg pitches
+    the scene toward the camera (top view > 0, bottom view < 0)."""
     depth = render_depth(np.deg2rad(view * step_deg), intr=intr, scale=scale, backdrop=backdrop,
-                         seed=1000 + view, noise=noise)
+                         seed=1000 + view + (7000 if tilt_deg else 0), noise=noise, tilt_rad=np.deg2rad(tilt_deg))
     return backproject(depth, intr=intr, scale=scale)
+
+
+# BASELINE configs[3]: Kinect-v2 frustum sampled on a 1344 x 1113 grid (~1.5 M valid pixels with the
+# full backdrop): the "super-resolution-densified" stress size of SURVEY 8(d)
+KV2_SR_SCALE = 1344.0 / 512.0
+
+
+def kinect_v2_sr_view(view: int, step_deg: float = 15.0, backdrop: str = "full", tilt_deg: float = 0.0) -> np.ndarray:
+    return kinect_view(view, step_deg=step_deg, scale=KV2_SR_SCALE, backdrop=backdrop, intr=KINECT_V2, tilt_deg=tilt_deg)
+
+
+def tilt_motion(tilt_deg: float, unit_scale: float = 0.001) -> np.ndarray:
+    """Ground-truth 4x4 taking a view rendered with `tilt_deg` onto the untilted frame: the scene
+    was pitched by +tilt about X through the table centre, so the cloud has to be pitched back."""
+    R = _rot_x(np.deg2rad(-tilt_deg))
+    c = TABLE_CENTRE_MM * unit_scale
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = c - R @ c
+    return T
 
 
 def turntable_motion(step_deg: float, unit_scale: float = 0.001) -> np.ndarray:

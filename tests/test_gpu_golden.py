@@ -64,3 +64,33 @@ def test_full_size_properties(ctx):
     k1, _, _ = api.sor(tgt, 50, 1.0, ctx=ctx)
     k2, _, _ = api.sor(tgt, 50, 1.0, negative=True, ctx=ctx)
     assert len(k1) + len(k2) == len(tgt) and not np.intersect1d(k1, k2).size
+
+
+def test_cuda_matches_independent_golden(ctx):
+    """The fixture of tests/golden/make_golden_independent.py (numpy / scipy, no oracle code):
+    correspondences bit-exact at two iterations, iteration counts and convergence states equal —
+    including the TRANSFORM and ABS_MSE exits — transforms / fitness within the north-star bars."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_independent.npz"))
+    src, tgt = g["src"], g["tgt"]
+    idx, d2 = api.nn(tgt, src, 0.02, ctx=ctx)
+    assert np.array_equal(idx, g["nn_idx"]) and np.array_equal(d2[idx >= 0], g["nn_d2"][idx >= 0])
+    T = HostCloud(tgt, normal=g["normals"], curvature=g["curvature"])
+    extent = float(np.ptp(tgt, axis=0).max())
+    for name, mode in (("p2p", 0), ("p2plane", 1)):
+        for it in (0, 3):
+            r = api.icp_align(src, T, 0.02, 50, mode=mode, dump_iteration=it, ctx=ctx)
+            assert np.array_equal(r["corr_index"], g[f"icp_{name}_corr{it}"]), (name, it)
+        assert [r["iterations"], r["state"]] == g[f"icp_{name}_meta"].tolist()
+        assert np.abs(r["transformation"] - g[f"icp_{name}_T"])[:3, :3].max() < 1e-5
+        assert np.abs(r["transformation"] - g[f"icp_{name}_T"])[:3, 3].max() < 1e-5 * extent
+        assert abs(r["fitness"] - g[f"icp_{name}_fitness"][0]) <= 1e-5 * r["fitness"]
+    r = api.icp_align(src, T, 0.02, 50, transformation_epsilon=1e-5, euclidean_fitness_epsilon=0.0, mode=1, ctx=ctx)
+    assert [r["iterations"], r["state"]] == g["icp_transform_exit_meta"].tolist() and r["state"] == 2
+    assert np.abs(r["transformation"] - g["icp_transform_exit_T"]).max() < 1e-5
+    r = api.icp_align(g["near"], tgt, 0.02, 50, transformation_epsilon=0.0, euclidean_fitness_epsilon=0.0, mode=0,
+                      ctx=ctx)
+    assert [r["iterations"], r["state"]] == g["icp_abs_mse_exit_meta"].tolist() and r["state"] == 3
+    kept, mean, _ = api.sor(tgt, 10, 1.0, ctx=ctx)
+    assert np.array_equal(kept, g["sor_kept"]) and np.array_equal(mean, g["sor_mean"])
+    v = api.voxel_grid(tgt, 0.02, ctx=ctx)
+    assert np.array_equal(v["voxel_of_point"], g["vox_of_point"]) and np.abs(v["xyz"] - g["vox_xyz"]).max() < 1e-6

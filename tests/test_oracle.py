@@ -348,3 +348,35 @@ def test_fitness_score_is_the_unbounded_mean_nn_distance(pair):
     d2 = cKDTree(tgt.astype(np.float64)).query(reg.astype(np.float64))[0] ** 2
     assert abs(r["fitness"] - d2.mean()) <= 1e-6 * d2.mean()
     assert (d2 > 0.02 ** 2).any()          # the sum really includes points beyond the gate
+
+
+# ------------------------------------------------------------------ independent golden fixture
+
+def test_oracle_matches_independent_golden():
+    """tests/golden/golden_independent.npz comes from tests/golden/make_golden_independent.py — a
+    numpy / scipy implementation that shares no code with the oracle.  Index sets bit-exact,
+    float32 distances bit-exact, transforms / fitness within the north-star tolerances, all five
+    convergence exits of DefaultConvergenceCriteria that the fixtures reach."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_independent.npz"))
+    src, tgt = g["src"], g["tgt"]
+    oi, od = orc.KdTree(tgt).nn(src, 0.02)
+    assert np.array_equal(oi, g["nn_idx"])
+    assert np.array_equal(od[oi >= 0], g["nn_d2"][oi >= 0])
+    T = HostCloud(tgt, normal=g["normals"], curvature=g["curvature"])
+    extent = float(np.ptp(tgt, axis=0).max())
+    for name, mode in (("p2p", 0), ("p2plane", 1)):
+        for it in (0, 3):
+            r = orc.icp_align(src, T, 0.02, 50, mode=mode, dump_iteration=it)
+            assert np.array_equal(r["corr_index"], g[f"icp_{name}_corr{it}"]), (name, it)
+        assert [r["iterations"], r["state"]] == g[f"icp_{name}_meta"].tolist()
+        assert np.abs(r["transformation"] - g[f"icp_{name}_T"])[:3, :3].max() < 1e-5
+        assert np.abs(r["transformation"] - g[f"icp_{name}_T"])[:3, 3].max() < 1e-5 * extent
+        assert abs(r["fitness"] - g[f"icp_{name}_fitness"][0]) <= 1e-5 * r["fitness"]
+    r = orc.icp_align(src, T, 0.02, 50, transformation_epsilon=1e-5, euclidean_fitness_epsilon=0.0, mode=1)
+    assert [r["iterations"], r["state"]] == g["icp_transform_exit_meta"].tolist() and r["state"] == 2
+    r = orc.icp_align(g["near"], tgt, 0.02, 50, transformation_epsilon=0.0, euclidean_fitness_epsilon=0.0, mode=0)
+    assert [r["iterations"], r["state"]] == g["icp_abs_mse_exit_meta"].tolist() and r["state"] == 3
+    kept, mean, st = orc.sor(tgt, 10, 1.0)
+    assert np.array_equal(kept, g["sor_kept"]) and np.array_equal(mean, g["sor_mean"])
+    v = orc.voxel_grid(tgt, 0.02)
+    assert np.array_equal(v["voxel_of_point"], g["vox_of_point"]) and np.abs(v["xyz"] - g["vox_xyz"]).max() < 1e-6
