@@ -30,7 +30,10 @@ extern "C" {
 /* A host point cloud described by base pointers + byte strides, so that both the
  * PCL in-memory layout (pcl::PointXYZRGBNormal, 48-byte AoS: xyz at +0, normal at
  * +16, rgba at +32, curvature at +36) and packed SoA arrays are accepted.
- * normal / rgba / curvature may be NULL when the operation does not need them. */
+ * normal / rgba / curvature may be NULL when the operation does not need them.
+ * Alignment: every stride must be a multiple of 4 bytes (the records are unpacked on the
+ * device with 4-byte loads); a layout that violates this is rejected with LC3D_ERR_INVALID.
+ * The base pointers themselves need no particular alignment. */
 typedef struct lc3d_cloud {
   int64_t n;
   const float* xyz;
@@ -61,6 +64,13 @@ const char* lc3d_version(void);
 void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]);
 /* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
 int64_t lc3d_launch_count(const lc3d_ctx* ctx);
+
+/* Page-locks / releases a caller-owned host range (cudaHostRegister): copies from / to it are
+ * then true asynchronous DMA at full PCIe rate instead of staged pageable copies.  Worth it for
+ * buffers that cross PCIe more than once (pinning costs about as much as one pageable copy).
+ * Optional: every entry point also accepts pageable memory. */
+int lc3d_host_register(void* ptr, uint64_t bytes);
+int lc3d_host_unregister(void* ptr);
 
 int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out);
 void lc3d_cloud_free(lc3d_ctx* ctx, lc3d_dcloud* dc);

@@ -93,7 +93,7 @@ SYMBOLS = [
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
     "lc3d_voxel_grid", "lc3d_sor", "lc3d_transform", "lc3d_box_dedup", "lc3d_euclidean_clusters",
-    "lc3d_prepare_view", "lc3d_cloud_download",
+    "lc3d_prepare_view", "lc3d_cloud_download", "lc3d_host_register", "lc3d_host_unregister",
 ]
 
 
@@ -192,6 +192,10 @@ def _declare(lib):
     lib.lc3d_prepare_view.restype = C.c_int
     lib.lc3d_cloud_download.argtypes = [vp, vp, vp, vp, vp]
     lib.lc3d_cloud_download.restype = C.c_int
+    lib.lc3d_host_register.argtypes = [vp, C.c_uint64]
+    lib.lc3d_host_register.restype = C.c_int
+    lib.lc3d_host_unregister.argtypes = [vp]
+    lib.lc3d_host_unregister.restype = C.c_int
     return lib
 
 

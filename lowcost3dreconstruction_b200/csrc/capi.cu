@@ -84,15 +84,19 @@ PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, b
   if (n == 0) return pu;
   if (n > (int64_t)INT32_MAX / 2) throw CudaError{"cloud too large (n must be < 2^30)"};
   if (!h->xyz || h->xyz_stride < 12) throw CudaError{"cloud.xyz is NULL or xyz_stride < 12"};
+  // the device unpacks the staged records with 4-byte loads: strides (and the offset between fields of
+  // one record) must keep every float 4-byte aligned
+  if (h->xyz_stride % 4 != 0) throw CudaError{"cloud.xyz_stride must be a multiple of 4 bytes"};
   d->xyz.ensure((size_t)n * 16);
   if (want_normals && h->normal) {
     if (h->normal_stride < 12) throw CudaError{"normal_stride < 12"};
+    if (h->normal_stride % 4 != 0) throw CudaError{"cloud.normal_stride must be a multiple of 4 bytes"};
     d->normal.ensure((size_t)n * 16);
   }
   // same AoS block as xyz (PCL 48-byte points)?  then one staged copy carries both
   const ptrdiff_t off = h->normal ? (const char*)h->normal - (const char*)h->xyz : -1;
   const bool same_block = want_normals && h->normal && h->normal_stride == h->xyz_stride && off >= 0 &&
-                          off + 12 <= h->xyz_stride;
+                          off + 12 <= h->xyz_stride && off % 4 == 0;
   pu.raw_xyz = stage_raw(ctx, raw_a, h->xyz, h->xyz_stride, n, same_block ? (int)off + 12 : 12, cs);
   if (want_normals && h->normal) {
     if (same_block)
@@ -454,6 +458,7 @@ template <typename F>
 int guarded(lc3d_ctx* ctx, F&& f) {
   if (!ctx) return LC3D_ERR_INVALID;
   try {
+    ctx->err.clear();
     Guard g(ctx);
     f();
     return LC3D_OK;
@@ -465,6 +470,12 @@ int guarded(lc3d_ctx* ctx, F&& f) {
     ctx->err = e.what();
     return LC3D_ERR_INTERNAL;
   }
+}
+
+// argument validation failure: the message is what lc3d_last_error returns
+int invalid(lc3d_ctx* ctx, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return LC3D_ERR_INVALID;
 }
 
 struct TmpClouds {
@@ -565,6 +576,26 @@ void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]) {
   out[5] = g.n;
 }
 
+int lc3d_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return LC3D_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return LC3D_ERR_CUDA;
+  }
+  return LC3D_OK;
+}
+
+int lc3d_host_unregister(void* ptr) {
+  if (!ptr) return LC3D_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return LC3D_ERR_CUDA;
+  }
+  return LC3D_OK;
+}
+
 int lc3d_cloud_upload(lc3d_ctx* ctx, const lc3d_cloud* host, lc3d_dcloud** out) {
   if (!out || !host) return LC3D_ERR_INVALID;
   *out = nullptr;
@@ -604,7 +635,7 @@ int64_t lc3d_dcloud_size(const lc3d_dcloud* dc) { return dc ? dc->n : 0; }
 int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* target,
                    const lc3d_icp_params* params, lc3d_icp_result* result,
                    const lc3d_icp_outputs* outputs) {
-  if (!source || !target || !params || !result) return LC3D_ERR_INVALID;
+  if (!source || !target || !params || !result) return invalid(ctx, "lc3d_icp_align: NULL argument");
   return guarded(ctx, [&] {
     std::memset(result, 0, sizeof *result);
     TmpClouds tc = tmp_clouds(ctx);
@@ -645,7 +676,7 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
 int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d_dcloud* target,
                             const lc3d_icp_params* params, lc3d_icp_result* result,
                             const lc3d_icp_outputs* outputs) {
-  if (!source || !target || !params || !result) return LC3D_ERR_INVALID;
+  if (!source || !target || !params || !result) return invalid(ctx, "lc3d_icp_align_resident: NULL argument");
   return guarded(ctx, [&] {
     std::memset(result, 0, sizeof *result);
     ctx->tm[5].start(ctx->stream);
@@ -655,7 +686,7 @@ int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d
 
 int lc3d_nn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, double max_dist,
             int32_t* out_index, float* out_dist2) {
-  if (!cloud || !out_index || !out_dist2) return LC3D_ERR_INVALID;
+  if (!cloud || !out_index || !out_dist2) return invalid(ctx, "lc3d_nn: NULL argument");
   return guarded(ctx, [&] {
     TmpClouds tc = tmp_clouds(ctx);
     upload_cloud(ctx, cloud, &tc.b, false);
@@ -685,7 +716,7 @@ int lc3d_nn(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_cloud* queries, d
 
 int lc3d_transform(lc3d_ctx* ctx, const lc3d_cloud* cloud, const float matrix[16], float* out_xyz,
                    float* out_normal) {
-  if (!cloud || !matrix || !out_xyz) return LC3D_ERR_INVALID;
+  if (!cloud || !matrix || !out_xyz) return invalid(ctx, "lc3d_transform: NULL argument");
   return guarded(ctx, [&] {
     TmpClouds tc = tmp_clouds(ctx);
     upload_cloud(ctx, cloud, &tc.a, out_normal != nullptr);

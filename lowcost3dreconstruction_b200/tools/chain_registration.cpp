@@ -7,6 +7,14 @@
 // contiguous blocks over the visible GPUs, one thread + one lc3d_ctx per device; only the 4x4
 // results meet on the host.  Not part of the reference; built on the same C ABI as the four
 // drop-in tools.
+//
+// In-process view pipeline: with --leaf_size / --neighbors / --normals the
+// per-view stages that scripts/alignment.sh:99-100 runs as separate processes with a PLY file
+// between each (outlier_removal, normal estimation; VoxelGrid for the turntable chain) run on the
+// device right after the load — lc3d_prepare_view — and the pairwise ICP works on the resident
+// results (lc3d_icp_align_resident): one PLY read and one PLY write per view, nothing in between.
+// The loaded views are page-locked (lc3d_host_register) because each one crosses PCIe more than
+// once (as source, as target, and for the final transform).
 #include <thread>
 
 #include "cli_common.hpp"
@@ -42,6 +50,10 @@ int main(int argc, char* argv[]) {
         .value("transformation_epsilon", 0, "Transformation epsilon", "1.0000000000000001e-09")
         .value("euclidean_fitness_epsilon", 0, "Euclidean fitness epsilon", "0.001")
         .flag("point_to_plane", 0, "Point-to-plane ICP using the target views' normals")
+        .value("leaf_size", 's', "In-process pcl::VoxelGrid leaf size per view (0 = off)", "0")
+        .value("neighbors", 0, "In-process StatisticalOutlierRemoval: number of neighbours (0 = off)", "0")
+        .value("dev_mult", 0, "In-process StatisticalOutlierRemoval: standard deviation multiplier", "1")
+        .value("normals", 0, "In-process normal estimation: number of neighbours (0 = keep the PLY's normals)", "0")
         .value("gpus", 'g', "Number of GPUs to use", "1");
     opt.parse(argc, argv);
     if (opt.count("help")) {
@@ -66,6 +78,15 @@ int main(int argc, char* argv[]) {
     prm.compute_fitness = 1;
     prm.dump_iteration = -1;
     const int gpus = std::max(1, opt.as<int>("gpus"));
+    lc3d_prepare_params prep{};
+    prep.leaf_size = opt.as<float>("leaf_size");
+    prep.sor_mean_k = opt.as<int>("neighbors");
+    prep.sor_stddev_mul = opt.as<double>("dev_mult");
+    prep.normals_k = opt.as<int>("normals");
+    const bool pipeline = prep.leaf_size > 0.0f || prep.sor_mean_k > 0 || prep.normals_k > 0;
+    if (prm.mode == LC3D_ICP_POINT_TO_PLANE && pipeline && prep.normals_k <= 0)
+      throw std::logic_error("--point_to_plane after --leaf_size/--neighbors needs --normals (the filtered views "
+                             "carry no normals).");
 
     std::vector<Cloud> views((size_t)n);
     for (int i = 0; i < n; ++i) {
@@ -74,6 +95,10 @@ int main(int argc, char* argv[]) {
       std::cout << "Loaded " << views[(size_t)i].size() << " data points from " << f << std::endl;
     }
 
+    // page-lock the loaded views: each crosses PCIe two or three times (source, target, transform)
+    for (auto& v : views)
+      if (v.size() > 0) lc3d_host_register(v.points.data(), v.size() * sizeof(Point));
+    std::vector<Cloud> filtered(pipeline ? (size_t)n : 0);
     // ---- pairs i -> i-1, contiguous blocks per device -----------------------------------------
     const int n_pairs = n - 1;
     std::vector<PairResult> res((size_t)n_pairs);
@@ -83,10 +108,49 @@ int main(int argc, char* argv[]) {
         for (int p = first; p < first + count; ++p) res[(size_t)p].error = lc3d_last_error(nullptr);
         return;
       }
-      for (int p = first; p < first + count; ++p) {  // pair index p registers view p+1 onto view p
-        const lc3d_cloud s = as_lc3d(views[(size_t)p + 1]), t = as_lc3d(views[(size_t)p]);
-        if (lc3d_icp_align(ctx, &s, &t, &prm, &res[(size_t)p].r, nullptr) != LC3D_OK)
-          res[(size_t)p].error = lc3d_last_error(ctx);
+      if (!pipeline) {
+        for (int p = first; p < first + count; ++p) {  // pair index p registers view p+1 onto view p
+          const lc3d_cloud s = as_lc3d(views[(size_t)p + 1]), t = as_lc3d(views[(size_t)p]);
+          if (lc3d_icp_align(ctx, &s, &t, &prm, &res[(size_t)p].r, nullptr) != LC3D_OK)
+            res[(size_t)p].error = lc3d_last_error(ctx);
+        }
+      } else {
+        // views first .. first+count prepared on the device (each once), pairs on the resident results;
+        // the filtered views come back to the host for the final transform + write
+        lc3d_dcloud* prev = nullptr;
+        for (int v = first; v <= first + count; ++v) {
+          const lc3d_cloud c = as_lc3d(views[(size_t)v], false);
+          lc3d_dcloud* cur = nullptr;
+          int64_t cnt[3] = {0, 0, 0};
+          std::string err;
+          if (lc3d_prepare_view(ctx, &c, &prep, &cur, cnt) != LC3D_OK) err = lc3d_last_error(ctx);
+          if (err.empty() && v > first &&
+              lc3d_icp_align_resident(ctx, cur, prev, &prm, &res[(size_t)v - 1].r, nullptr) != LC3D_OK)
+            err = lc3d_last_error(ctx);
+          // the block's first view is downloaded by its own block only when it is view 0 or this is
+          // the block that registers it; shared border views are written by the block that sources them
+          if (err.empty() && (v > first || v == 0)) {
+            Cloud& dst = filtered[(size_t)v];
+            const size_t m = (size_t)cnt[2];
+            std::vector<float> xyz(3 * m + 3), nrm(3 * m + 3), curv(m + 1);
+            if (m > 0 && lc3d_cloud_download(ctx, cur, xyz.data(), nrm.data(), curv.data()) != LC3D_OK)
+              err = lc3d_last_error(ctx);
+            dst.points.assign(m, Point{});
+            for (size_t k = 0; k < m; ++k) {
+              Point& p = dst.points[k];
+              p.x = xyz[3 * k]; p.y = xyz[3 * k + 1]; p.z = xyz[3 * k + 2]; p.w = 1.0f;
+              if (prep.normals_k > 0) { p.nx = nrm[3 * k]; p.ny = nrm[3 * k + 1]; p.nz = nrm[3 * k + 2]; p.curvature = curv[k]; }
+              p.rgba = 0xff808080u;
+            }
+            dst.width = (uint32_t)m; dst.height = 1; dst.is_dense = true;
+          }
+          if (!err.empty())
+            for (int p = std::max(v - 1, first); p < first + count; ++p) res[(size_t)p].error = err;
+          lc3d_cloud_free(ctx, prev);
+          prev = cur;
+          if (!err.empty()) break;
+        }
+        lc3d_cloud_free(ctx, prev);
       }
       lc3d_destroy(ctx);
     };
@@ -104,6 +168,9 @@ int main(int argc, char* argv[]) {
     for (int p = 0; p < n_pairs; ++p)
       if (!res[(size_t)p].error.empty()) throw std::runtime_error("lc3d: " + res[(size_t)p].error);
 
+    for (auto& v : views)
+      if (v.size() > 0) lc3d_host_unregister(v.points.data());
+    if (pipeline) views.swap(filtered);  // what gets transformed and written are the filtered views
     // ---- compose, apply, write ---------------------------------------------------------------
     Ctx ctx;
     double G[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};

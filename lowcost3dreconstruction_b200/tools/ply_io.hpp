@@ -191,7 +191,8 @@ inline Slot slot_of(const std::string& n) {
   return S_NONE;
 }
 inline void assign(Point& p, Slot s, double v, Type t, const unsigned char* raw) {
-  auto byte = [](double d) { return (uint32_t)(d < 0 ? 0 : d > 255 ? 255 : d); };
+  // NaN colour channels become 0 (a NaN -> unsigned conversion would be undefined behaviour)
+  auto byte = [](double d) { return (uint32_t)(!(d > 0) ? 0 : d > 255 ? 255 : d); };
   switch (s) {
     case S_X: p.x = (float)v; break;
     case S_Y: p.y = (float)v; break;
@@ -420,19 +421,33 @@ inline int load_ply(const std::string& path, Cloud& cloud, std::string* err = nu
           done += n;
         }
       } else {
+        // an element with a list property has no fixed record size: walk it property by property.
+        // A VERTEX element of this kind still contributes its scalar properties (as the ASCII
+        // path does); list entries are skipped.
         unsigned char tmp[8];
-        for (size_t i = 0; i < e.count; ++i)
-          for (const Property& p : e.props) {
+        for (size_t i = 0; i < e.count; ++i) {
+          Point pt{};
+          pt.w = 1.0f;
+          pt.rgba = 0xff000000u;
+          for (size_t k = 0; k < e.props.size(); ++k) {
+            const Property& p = e.props[k];
             if (p.is_list) {
               in.read(reinterpret_cast<char*>(tmp), type_size(p.count_type));
               if (!in) return fail("truncated PLY data");
               long cnt = (long)read_bin(tmp, p.count_type);
+              if (cnt < 0) return fail("negative list length in PLY data");
               in.ignore((std::streamsize)cnt * type_size(p.type));
+            } else if (is_vertex && slots[k] != S_NONE) {
+              in.read(reinterpret_cast<char*>(tmp), type_size(p.type));
+              if (!in) return fail("truncated PLY data");
+              assign(pt, slots[k], read_bin(tmp, p.type), p.type, tmp);
             } else {
               in.ignore(type_size(p.type));
             }
             if (!in) return fail("truncated PLY data");
           }
+          if (is_vertex) cloud.points.push_back(pt);
+        }
       }
     }
   }

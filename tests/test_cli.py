@@ -256,3 +256,72 @@ def test_cluster_extraction_matches_oracle(tmp_path):
     # nothing large enough: the reference's error path
     rc, out, err = run("cluster_extraction", "-i", i, "-o", o, "-t", "0.0001", "-p", "0.9")
     assert rc == 255 and err.strip() == "Could not extact clusters for the given dataset"
+
+
+# ------------------------------------------------------------------ transform
+
+def test_transform_cli_contract(tmp_path):
+    """pcl_tools/transform.cpp: options, usage line, matrix-file errors (no GPU needed)."""
+    rc, out, _ = run("transform", "--help")
+    assert rc == 0 and out.startswith("Transforms Point cloud.\n\nOptions:")
+    assert "-t [ --transform ] arg" in out and "File containing a 4x4 transformation matrix" in out
+    rc, _, err = run("transform", "-i", "a.ply", "-o", "b.ply")
+    assert rc == 255 and err.startswith("Correct mode of use: ")
+    assert err.strip().endswith("-i input.ply -o output.ply -t transform_file.txt")
+    rc, _, err = run("transform", "-i", "/nonexistent.ply", "-o", "b.ply", "-t", "m.txt")
+    assert rc == 255 and err.strip() == "Couldn't load input point cloud: /nonexistent.ply"
+    pts = synth.kinect_view(0, scale=0.05)
+    src = str(tmp_path / "in.ply")
+    plyutil.write_capture_ascii(src, pts)
+    rc, _, err = run("transform", "-i", src, "-o", str(tmp_path / "o.ply"), "-t", str(tmp_path / "missing.txt"))
+    assert rc == 255 and err.strip() == "Unable to open file: " + str(tmp_path / "missing.txt")
+    bad = tmp_path / "bad.txt"
+    bad.write_text("1 0 0 0\n0 1 0 0\n0 0 1\n")
+    rc, _, err = run("transform", "-i", src, "-o", str(tmp_path / "o.ply"), "-t", str(bad))
+    assert rc == 255 and err.strip() == "Error on read transform file: " + str(bad)
+
+
+@pytest.mark.gpu
+def test_transform_and_chain_pipeline_end_to_end(tmp_path, ctx):
+    from lowcost3dreconstruction_b200 import api, chain
+    # transform: matrix file in, points + normals out, equal to the library call
+    pts = synth.kinect_view(0, scale=0.25, backdrop="none")
+    nrm, curv = api.normals(pts, 15, ctx=ctx)
+    src, dst, mat = str(tmp_path / "in.ply"), str(tmp_path / "out.ply"), str(tmp_path / "T.txt")
+    plyutil.write_capture_ascii(src, pts, normals=nrm)
+    T = synth.rigid(3.0, -8.0, 1.5, [0.01, -0.02, 0.03])
+    chain.write_matrix_file(mat, T)
+    rc, _, err = run("transform", "-i", src, "-o", dst, "-t", mat)
+    assert rc == 0, err
+    loaded = plyutil.read_pcl_binary(src if False else dst)
+    inp_xyz = np.round(pts.astype(np.float64), 6).astype(np.float32)  # the ASCII writer keeps 6 decimals
+    inp_nrm = np.round(nrm.astype(np.float64), 6).astype(np.float32)
+    from lowcost3dreconstruction_b200._capi import HostCloud
+    gx, gn = api.transform(HostCloud(inp_xyz, normal=inp_nrm), chain.read_matrix_file(mat).astype(np.float32), ctx=ctx)
+    assert np.array_equal(loaded["xyz"], gx) and np.array_equal(loaded["normal"], gn)
+    # chain_registration with the in-process pipeline == prepare_view + resident ICP through the API
+    views = [synth.apply_transform(synth.turntable_prior(v, 10.0), synth.kinect_view(v, step_deg=10.0, scale=0.5, backdrop="none"))
+             for v in range(3)]
+    d = tmp_path / "views"
+    d.mkdir()
+    for v, c in enumerate(views):
+        plyutil.write_capture_ascii(str(d / f"{v}.ply"), c)
+    o = tmp_path / "reg"
+    o.mkdir()
+    rc, out, err = run("chain_registration", "-n", "3", "-d", str(d), "-o", str(o), "--distance_threshold", "0.02",
+                       "--point_to_plane", "--leaf_size", "0.004", "--neighbors", "20", "--dev_mult", "2.0", "--normals", "15")
+    assert rc == 0, err
+    loaded = [np.array(plyutil.read_pcl_binary(str(d / f"{v}.ply"))["xyz"]) if False else
+              np.round(c.astype(np.float64), 6).astype(np.float32) for v, c in enumerate(views)]
+    prep = [api.prepare_view(c, 0.004, 20, 2.0, 15, ctx=ctx)[0] for c in loaded]
+    G = np.eye(4)
+    first = plyutil.read_pcl_binary(str(o / "0.ply"))
+    assert np.array_equal(first["xyz"], prep[0].download()[0])
+    for v in (1, 2):
+        r = api.icp_align(prep[v], prep[v - 1], 0.02, 50, mode=api.POINT_TO_PLANE, ctx=ctx)
+        G = G @ r["transformation"].astype(np.float64)
+        assert np.allclose(chain.read_matrix_file(str(o / f"fine_{v}.txt")), G, atol=1e-7)
+        x, n, _ = prep[v].download()
+        gx, gn = api.transform(HostCloud(x, normal=n), G.astype(np.float32), ctx=ctx)
+        w = plyutil.read_pcl_binary(str(o / f"{v}.ply"))
+        assert np.array_equal(w["xyz"], gx) and np.array_equal(w["normal"], gn)
