@@ -56,6 +56,7 @@ struct Grid {
   GridDev v{};
   DevBuf cell_start, coarse_cnt, pts, nrm, occ_raw, occ;
   int64_t ncell = 0;
+  double pts_per_cell_est = 0.0;  // (cell edge / point spacing)^2 / x subdivision, from the density probe
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   void release() {
     cell_start.release();
@@ -202,11 +203,12 @@ __global__ void __launch_bounds__(256)
     grid_keys(const float4* __restrict__ p, int n, GridDev g, uint32_t ncell,
               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
               uint32_t* __restrict__ cell_cnt, uint32_t* __restrict__ coarse_cnt,
-              uint32_t* __restrict__ occ_bits = nullptr, int occ_wx = 0) {
+              uint32_t* __restrict__ occ_bits = nullptr, int occ_wx = 0, uint32_t* __restrict__ rank = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = p[i];
   uint32_t key = ncell;
+  uint32_t my_rank = 0;
   if (finite3(q.x, q.y, q.z)) {
     int ix = min(max((int)floorf(cell_coord(q.x, g.ox, g.inv_cx)), 0), g.dx - 1);
     int iy = min(max((int)floorf(cell_coord(q.y, g.oy, g.inv_c)), 0), g.dy - 1);
@@ -217,8 +219,14 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const unsigned act = __activemask();
     if (cell_cnt) {
+      // the value the atomic returns is this warp's first slot in the cell: a (run-dependent) rank
+      // inside the cell for the counting sort; the order is made canonical afterwards
       const unsigned peers = __match_any_sync(act, key);
-      if (lane == __ffs(peers) - 1) atomicAdd(&cell_cnt[key], (uint32_t)__popc(peers));
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&cell_cnt[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      my_rank = base + __popc(peers & ((1u << lane) - 1u));
     }
     if (coarse_cnt) {
       const uint32_t ck = (uint32_t)(((iz >> kCoarseShift) * g.cdy + (iy >> kCoarseShift)) * g.cdx +
@@ -234,9 +242,47 @@ __global__ void __launch_bounds__(256)
       const uint32_t combined = __reduce_or_sync(peers, m);
       if (lane == __ffs(peers) - 1 && (occ_bits[word] & combined) != combined) atomicOr(&occ_bits[word], combined);
     }
+  } else if (rank) {
+    my_rank = atomicAdd(&cell_cnt[ncell], 1u);  // non-finite points: sentinel cell, sorted last
   }
   keys[i] = key;
-  vals[i] = (uint32_t)i;
+  if (rank)
+    rank[i] = my_rank;
+  else
+    vals[i] = (uint32_t)i;
+}
+
+// ---- counting sort by cell: scatter with the atomic ranks, then canonical order ---------------
+// tmp[start[key] + rank] = point index: groups the points by cell in a run-dependent order.
+__global__ void __launch_bounds__(256)
+    cs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ start,
+               int n, uint32_t* __restrict__ tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tmp[start[keys[i]] + rank[i]] = (uint32_t)i;
+}
+// Canonical (= stable) order inside every cell: the final slot of point i is its cell's start plus
+// the number of points of the same cell with a smaller index (cells hold a handful of points, so
+// the count is a short scan of the cell's segment); the point (and its normal) is written there.
+// The layout is thereby identical to a stable sort by cell, whatever order the atomics ran in.
+__global__ void __launch_bounds__(256)
+    cs_fixup_gather(const uint32_t* __restrict__ tmp, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ start,
+                    const float4* __restrict__ p, const float4* __restrict__ nrm, int n, float4* __restrict__ out_p,
+                    float4* __restrict__ out_n, float4* __restrict__ out_p2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t i = tmp[t];
+  const uint32_t key = keys[i];
+  const uint32_t s = start[key], e = start[key + 1];
+  uint32_t r = t - s;  // pathological cells (thousands of coincident points) keep the scattered order
+  if (e - s <= 4096u) {
+    r = 0;
+    for (uint32_t u = s; u < e; ++u) r += tmp[u] < i ? 1u : 0u;
+  }
+  float4 q = p[i];
+  q.w = __int_as_float((int)i);
+  out_p[s + r] = q;
+  if (out_p2) out_p2[s + r] = q;
+  if (nrm) out_n[s + r] = nrm[i];
 }
 
 // Box dilation (Chebyshev radius r cells) of the occupancy bits: out bit = OR of all bits within r cells.
@@ -352,7 +398,7 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
     maxext = std::max(maxext, ext[d]);
   }
   // point spacing (surface area ~ occupied probe cells) -> cell edge
-  double cell;
+  double cell, spacing_est = 0.0;
   if (nfinite <= 1 || maxext <= 0) {
     cell = maxext > 0 ? maxext : 1.0;
   } else {
@@ -362,6 +408,7 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
     double cell_area = std::pow(pe[0] * pe[1] * pe[2], 2.0 / 3.0);
     double area = std::max(1.0, (double)occ) * cell_area;
     double spacing = std::sqrt(area / (double)nfinite);
+    spacing_est = spacing;
     cell = cell_factor * spacing;
   }
   cell = std::max(cell, min_cell);
@@ -406,6 +453,7 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
   g.cdz = (g.dz + kCoarse - 1) >> kCoarseShift;
   g.n = nfinite;
   G.ncell = (int64_t)g.dx * g.dy * g.dz;
+  G.pts_per_cell_est = spacing_est > 0 ? (cell / spacing_est) * (cell / spacing_est) / (double)xs : (double)nfinite;
 }
 
 // before_gather: called (stream-ordered on ctx->stream) right before the normals are first read,
@@ -418,12 +466,12 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
   GridDev& g = G.v;
   const int64_t ncoarse = (int64_t)g.cdx * g.cdy * g.cdz;
   // 3. keys + histograms
-  G.cell_start.ensure((size_t)(G.ncell + 2) * 4);
+  G.cell_start.ensure((size_t)(G.ncell + 4) * 4);
   G.coarse_cnt.ensure((size_t)ncoarse * 4);
   G.pts.ensure((size_t)n * 16 + 16);
   if (nrm) G.nrm.ensure((size_t)n * 16 + 16);
   uint32_t* cell_start = G.cell_start.as<uint32_t>();
-  LC3D_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(G.ncell + 2) * 4, st));
+  LC3D_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(G.ncell + 4) * 4, st));
   LC3D_CUDA(cudaMemsetAsync(G.coarse_cnt.p, 0, (size_t)ncoarse * 4, st));
   ctx->scratch[kScrKeys].ensure((size_t)n * 4);
   ctx->scratch[kScrVals].ensure((size_t)n * 4);
@@ -431,7 +479,7 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
   ctx->scratch[kScrValsAlt].ensure((size_t)n * 4);
   ctx->scratch[kScrHist].ensure(sort_hist_bytes(n));
   ctx->scratch[kScrScan].ensure(
-      std::max(scan_scratch_bytes(G.ncell + 2), scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile))) + 64);
+      std::max(scan_scratch_bytes(G.ncell + 4), scan_scratch_bytes((int64_t)kRadix * div_up(n, kSortTile))) + 64);
   uint32_t* keys = ctx->scratch[kScrKeys].as<uint32_t>();
   uint32_t* vals = ctx->scratch[kScrVals].as<uint32_t>();
   // dilated occupancy (rejects queries with nothing within occ_reach in O(1)): only for small radii
@@ -450,8 +498,34 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
   } else {
     occ_r = 0;
   }
+  // Counting sort (one histogram pass with atomic ranks, scan, scatter, canonical in-cell order)
+  // when cells hold a handful of points — the ICP / k-NN indexes; the multi-pass radix sort when a
+  // forced minimum cell edge packs hundreds of points into a cell (the in-cell ordering step is
+  // quadratic in the cell population).
+  const bool counting = G.pts_per_cell_est <= 192.0 && !std::getenv("LC3D_RADIX_INDEX");
   LC3D_LAUNCH(ctx, grid_keys, div_up(n, 256), 256, 0, xyz, n, g, (uint32_t)G.ncell, keys, vals,
-              cell_start, G.coarse_cnt.as<uint32_t>(), occ_raw, occ_wx);
+              cell_start, G.coarse_cnt.as<uint32_t>(), occ_raw, occ_wx, counting ? vals : (uint32_t*)nullptr);
+  if (counting) {
+    uint32_t* rank = vals;
+    uint32_t* tmp = ctx->scratch[kScrKeysAlt].as<uint32_t>();
+    exclusive_scan_u32(ctx, cell_start, cell_start, G.ncell + 2, ctx->scratch[kScrScan].as<uint32_t>());
+    LC3D_LAUNCH(ctx, cs_scatter, div_up(n, 256), 256, 0, keys, rank, cell_start, n, tmp);
+    if (occ_raw) {
+      LC3D_LAUNCH(ctx, occ_dilate, div_up((int64_t)occ_words, 256), 256, 0, occ_raw, G.occ.as<uint32_t>(), occ_wx, g.dy,
+                  g.dz, occ_r);
+      g.occ = G.occ.as<uint32_t>();
+      g.occ_wx = occ_wx;
+      g.occ_r = occ_r;
+    }
+    if (before_gather) before_gather();
+    LC3D_LAUNCH(ctx, cs_fixup_gather, div_up(n, 256), 256, 0, tmp, keys, cell_start, xyz, nrm, n, G.pts.as<float4>(),
+                nrm ? G.nrm.as<float4>() : nullptr, (float4*)nullptr);
+    g.cell_start = cell_start;
+    g.coarse_cnt = G.coarse_cnt.as<uint32_t>();
+    g.pts = G.pts.as<float4>();
+    g.nrm = nrm ? G.nrm.as<float4>() : nullptr;
+    return;
+  }
   if (occ_raw) {
     LC3D_LAUNCH(ctx, occ_dilate, div_up((int64_t)occ_words, 256), 256, 0, occ_raw, G.occ.as<uint32_t>(), occ_wx, g.dy, g.dz,
                 occ_r);
@@ -495,9 +569,11 @@ __device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
   v = (v | (v << 2)) & 0x09249249u;
   return v;
 }
+// hist != null: counting-sort mode — histogram of the keys with the atomic's return value as the
+// (run-dependent) rank inside the key, written to vals; otherwise vals = point index (radix mode).
 __global__ void __launch_bounds__(256)
     query_keys(const float4* __restrict__ p, int n, GridDev g, int shift, uint32_t sentinel,
-               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = p[i];
@@ -510,7 +586,17 @@ __global__ void __launch_bounds__(256)
           (morton_spread10((uint32_t)iz >> shift) << 2);
   }
   keys[i] = key;
-  vals[i] = (uint32_t)i;
+  if (hist) {
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    vals[i] = base + __popc(peers & ((1u << lane) - 1u));
+  } else {
+    vals[i] = (uint32_t)i;
+  }
 }
 
 // Needs only grid_plan's result.  scr: first of 6 consecutive scratch slots (keys, vals, alt
@@ -531,8 +617,31 @@ inline void sort_queries_by_cell(lc3d_ctx* ctx, const Grid& G, const float4* xyz
   int maxdim = std::max(G.v.dx >> G.v.xs_shift, std::max(G.v.dy, G.v.dz));
   int shift = 0;
   while ((maxdim >> shift) > 1024) ++shift;  // 10 bits per axis
+  // Counting sort over the Morton cells (histogram with atomic ranks, scan, scatter, canonical
+  // in-cell order: 5 launches instead of the 11 of a 3-pass radix sort).  The key table has
+  // 2^(3 bits-per-axis) entries, so the Morton cells are coarsened until it fits 2^22; cells that
+  // would then hold hundreds of points fall back to the radix sort.
+  int cshift = shift;
+  while (3 * bit_length((uint32_t)((maxdim - 1) >> cshift)) > 22) ++cshift;
+  const double per_key = G.pts_per_cell_est * (double)G.v.xs * std::pow(4.0, cshift);  // a surface: ~4^shift cells merge
+  if (per_key <= 256.0 && !std::getenv("LC3D_RADIX_INDEX")) {
+    const int cbc = bit_length((uint32_t)((maxdim - 1) >> cshift));
+    const int64_t nkeys = ((int64_t)1 << (3 * cbc)) + 1;  // + the non-finite sentinel
+    ctx->scratch[sHist].ensure((size_t)(nkeys + 4) * 4);
+    ctx->scratch[sScan].ensure(scan_scratch_bytes(nkeys + 4) + 64);
+    uint32_t* table = ctx->scratch[sHist].as<uint32_t>();
+    uint32_t* tmp = ctx->scratch[sKeysAlt].as<uint32_t>();
+    LC3D_CUDA(cudaMemsetAsync(table, 0, (size_t)(nkeys + 4) * 4, ctx->stream));
+    LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, cshift, (uint32_t)(nkeys - 1), keys, vals, table);
+    exclusive_scan_u32(ctx, table, table, nkeys + 1, ctx->scratch[sScan].as<uint32_t>());
+    LC3D_LAUNCH(ctx, cs_scatter, div_up(n, 256), 256, 0, keys, vals, table, n, tmp);
+    LC3D_LAUNCH(ctx, cs_fixup_gather, div_up(n, 256), 256, 0, tmp, keys, table, xyz, (const float4*)nullptr, n, out_sorted,
+                (float4*)nullptr, out_sorted2);
+    return;
+  }
   const int cb0 = bit_length((uint32_t)((maxdim - 1) >> shift));
-  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, (uint32_t)1u << (3 * cb0), keys, vals);
+  LC3D_LAUNCH(ctx, query_keys, div_up(n, 256), 256, 0, xyz, n, G.v, shift, (uint32_t)1u << (3 * cb0), keys, vals,
+              (uint32_t*)nullptr);
   SortScratch ss{ctx->scratch[sKeysAlt].as<uint32_t>(), ctx->scratch[sValsAlt].as<uint32_t>(),
                  ctx->scratch[sHist].as<uint32_t>(), ctx->scratch[sScan].as<uint32_t>()};
   // key bits actually used: 3 interleaved coordinates of bit_length((maxdim-1) >> shift) bits,

@@ -460,25 +460,41 @@ __global__ void __launch_bounds__(256)
   if (flags[i]) out[pos[i]] = i;
 }
 
-// pcl::compute3DCentroid: float32 sequential sum in input order / count.  Sequential by
-// definition (bit-parity with the float32 reference sum); one thread, L2-resident data.
-__global__ void centroid_kernel(const float4* __restrict__ xyz, int n, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// pcl::compute3DCentroid: float32 sum in input order / count.  The sum is sequential by
+// definition (bit-parity with the reference's float32 accumulation), but the loads are not: one
+// warp fetches 32 points at a time (one coalesced 512-byte request) and every lane then adds them
+// one by one in index order, so the result is the sequential sum while the memory latency is
+// paid once per 32 points.  Launch with ONE warp.
+__global__ void __launch_bounds__(32) centroid_kernel(const float4* __restrict__ xyz, int n, float* __restrict__ out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   int cnt = 0;
-  for (int i = 0; i < n; ++i) {
-    const float4 p = xyz[i];
-    if (!finite3(p.x, p.y, p.z)) continue;
-    sx += p.x;
-    sy += p.y;
-    sz += p.z;
-    ++cnt;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = false;
+    if (i < n) {
+      p = xyz[i];
+      ok = finite3(p.x, p.y, p.z);
+    }
+    unsigned m = __ballot_sync(full, ok);
+    cnt += __popc(m);
+    while (m) {  // ascending index order, non-finite points skipped as PCL does
+      const int k = __ffs(m) - 1;
+      m &= m - 1;
+      sx += __shfl_sync(full, p.x, k);
+      sy += __shfl_sync(full, p.y, k);
+      sz += __shfl_sync(full, p.z, k);
+    }
   }
-  const float fc = (float)cnt;
-  out[0] = sx / fc;
-  out[1] = sy / fc;
-  out[2] = sz / fc;
-  out[3] = 1.0f;
+  if (lane == 0) {
+    const float fc = (float)cnt;
+    out[0] = sx / fc;
+    out[1] = sy / fc;
+    out[2] = sz / fc;
+    out[3] = 1.0f;
+  }
 }
 
 }  // namespace lc3d

@@ -324,7 +324,7 @@ def test_sor_mask_bit_exact(ctx, pair, k, mul):
 
 # --------------------------------------------------------------------------- VoxelGrid
 
-@pytest.mark.parametrize("leaf", [0.002, 0.01, 0.05])
+@pytest.mark.parametrize("leaf", [0.002, 0.01, 0.05, 1.0])  # 1.0 = the CLI default: a handful of huge voxels
 def test_voxel_grid_bit_exact(ctx, pair_normals, leaf):
     _, tgt = pair_normals
     rng = np.random.default_rng(1)
@@ -438,3 +438,36 @@ def test_euclidean_clusters_edge_cases(ctx):
     same = np.zeros((100, 3), np.float32)                                                # duplicates
     lab, sz = api.euclidean_clusters(same, 1e-3, 1, 100, ctx=ctx)
     assert sz.tolist() == [100] and (lab == 0).all()
+
+
+# ------------------------------------------------------------------- ABI argument validation
+
+def test_abi_rejects_bad_layouts_with_a_message(ctx):
+    """Strides that are not multiples of 4 bytes would fault on the device (4-byte loads): they are
+    rejected up front with LC3D_ERR_INVALID and a message; so are non-positive k / leaf sizes."""
+    import ctypes as C
+    from lowcost3dreconstruction_b200 import _capi
+    lib = _capi.load()
+    raw = np.zeros(15 * 64 + 16, dtype=np.uint8)  # packed 15-byte xyz+rgb records
+    c = _capi.Cloud()
+    c.n, c.xyz, c.xyz_stride = 64, raw.ctypes.data, 15
+    idx = np.empty(64, np.int32)
+    d2 = np.empty(64, np.float32)
+    rc = lib.lc3d_nn(ctx._h, C.byref(c), None, 0.0, idx.ctypes.data, d2.ctypes.data)
+    assert rc == -1 and b"multiple of 4" in lib.lc3d_last_error(ctx._h)
+    pts = np.random.default_rng(0).uniform(-1, 1, (200, 3)).astype(np.float32)
+    with pytest.raises(api.Lc3dError, match="mean_k"):
+        api.sor(pts, 0, 1.0, ctx=ctx)
+    with pytest.raises(api.Lc3dError, match="neighbours must be positive"):
+        api.normals(pts, 0, ctx=ctx)
+    with pytest.raises(api.Lc3dError, match="leaf size"):
+        api.voxel_grid(pts, 0.0, ctx=ctx)
+    # the context stays usable after a rejected call (no sticky device error)
+    i2, _ = api.nn(pts, ctx=ctx)
+    assert np.array_equal(i2, np.arange(200))
+    # a resident source without normals returns no registered normals; mixing resident / host raises
+    ds, dt = ctx.upload(pts), ctx.upload(pts)
+    r = api.icp_align(ds, dt, 0.05, 5, want_registered=True, ctx=ctx)
+    assert "registered_normal" not in r and r["registered_xyz"].shape == (200, 3)
+    with pytest.raises(api.Lc3dError, match="both be resident"):
+        api.icp_align(ds, pts, 0.05, 5, ctx=ctx)
