@@ -144,6 +144,30 @@ int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d
                             const lc3d_icp_params* params, lc3d_icp_result* result,
                             const lc3d_icp_outputs* outputs);
 
+/* ------------------------------------- one pair over several GPUs -- */
+
+/* Second multi-GPU mode (the first is independent pairs, one per GPU): ONE large pair with the
+ * SOURCE sharded over `world` processes, one GPU each (at most 8), every rank holding the whole
+ * target.  Each rank's correspondence kernel writes its partial estimator sums into an exchange
+ * buffer the other ranks have mapped with CUDA IPC; the solve kernel of every rank reads all
+ * ranks' sums directly from peer memory over NVLink / NVSwitch, adds them in rank order and
+ * solves, so every rank obtains the bit-identical pose and convergence decision without a
+ * separate all-reduce or broadcast.  Correspondences are exactly those of the unsharded run;
+ * the pose differs from it only by the grouping of the fp64 sums.
+ *   1. every rank: lc3d_shard_export (allocates the exchange buffer, returns its 64-byte IPC handle)
+ *   2. the caller exchanges the handles (any transport: 64 bytes per rank)
+ *   3. every rank: lc3d_shard_connect with all handles
+ *   4. every rank, collectively, once per alignment: lc3d_icp_align_sharded.  The callers must
+ *      synchronise (a barrier) between two consecutive sharded alignments.
+ * fitness_sum_count (may be NULL) receives this shard's {sum of squared NN distances, points}: the
+ * fitness of the whole pair is sum(sums) / sum(counts) over the ranks. */
+int lc3d_shard_export(lc3d_ctx* ctx, int64_t max_shard_points, unsigned char handle_out[64]);
+int lc3d_shard_connect(lc3d_ctx* ctx, int32_t rank, int32_t world, const unsigned char* handles);
+int lc3d_icp_align_sharded(lc3d_ctx* ctx, const lc3d_dcloud* source_shard, const lc3d_dcloud* target,
+                           const lc3d_icp_params* params, lc3d_icp_result* result,
+                           const lc3d_icp_outputs* outputs, double fitness_sum_count[2]);
+void lc3d_shard_close(lc3d_ctx* ctx);
+
 /* ------------------------------------------------------ neighbour search ---- */
 
 /* Exact k nearest neighbours of every query among `cloud` (pcl::search::KdTree

@@ -94,6 +94,7 @@ SYMBOLS = [
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
     "lc3d_voxel_grid", "lc3d_sor", "lc3d_transform", "lc3d_box_dedup", "lc3d_euclidean_clusters",
     "lc3d_prepare_view", "lc3d_cloud_download", "lc3d_host_register", "lc3d_host_unregister",
+    "lc3d_shard_export", "lc3d_shard_connect", "lc3d_icp_align_sharded", "lc3d_shard_close",
 ]
 
 
@@ -196,6 +197,15 @@ def _declare(lib):
     lib.lc3d_host_register.restype = C.c_int
     lib.lc3d_host_unregister.argtypes = [vp]
     lib.lc3d_host_unregister.restype = C.c_int
+    lib.lc3d_shard_export.argtypes = [vp, i64, vp]
+    lib.lc3d_shard_export.restype = C.c_int
+    lib.lc3d_shard_connect.argtypes = [vp, i32, i32, vp]
+    lib.lc3d_shard_connect.restype = C.c_int
+    lib.lc3d_icp_align_sharded.argtypes = [vp, vp, vp, C.POINTER(IcpParams), C.POINTER(IcpResult),
+                                           C.POINTER(IcpOutputs), C.POINTER(C.c_double)]
+    lib.lc3d_icp_align_sharded.restype = C.c_int
+    lib.lc3d_shard_close.argtypes = [vp]
+    lib.lc3d_shard_close.restype = None
     return lib
 
 

@@ -107,3 +107,63 @@ def read_matrix_file(path: str) -> np.ndarray:
     if len(vals) < 16:
         raise ValueError(f"{path}: expected 16 numbers, found {len(vals)}")
     return np.array(vals[:16], dtype=np.float64).reshape(4, 4)
+
+
+# --------------------------------------------------------------------------------------------
+# Second multi-GPU mode: ONE large pair, the source sharded over the ranks.
+
+class ShardedPair:
+    """Source-sharded ICP of one pair over `world` processes (one GPU each; torch.distributed is the
+    control plane: it carries the 64-byte IPC handles once and the barrier between alignments — the
+    per-iteration exchange of the estimator sums happens inside the solve kernel over peer memory,
+    see include/lc3d.h).  Every rank passes its slice of the source and the WHOLE target."""
+
+    def __init__(self, ctx, max_shard_points: int):
+        import ctypes as C
+
+        import torch.distributed as dist
+        self.ctx, self.dist = ctx, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        handle = (C.c_ubyte * 64)()
+        ctx._check(ctx._lib.lc3d_shard_export(ctx._h, int(max_shard_points), handle), "lc3d_shard_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        blob = b"".join(handles)
+        ctx._check(ctx._lib.lc3d_shard_connect(ctx._h, self.rank, self.world, blob), "lc3d_shard_connect")
+        dist.barrier()
+
+    def shard(self, n: int) -> slice:
+        """this rank's contiguous slice of an n-point source"""
+        base, extra = divmod(n, self.world)
+        start = self.rank * base + min(self.rank, extra)
+        return slice(start, start + base + (1 if self.rank < extra else 0))
+
+    def align(self, src_shard, tgt, max_correspondence_distance=0.1, max_iterations=50, transformation_epsilon=1e-9,
+              euclidean_fitness_epsilon=1e-3, mode=0, dump_iteration=-1) -> dict:
+        """src_shard / tgt: api.DeviceCloud.  Collective.  Returns the api.icp_align result dict with the
+        fitness of the WHOLE pair (shard sums combined with one all_gather_object)."""
+        import ctypes as C
+
+        from . import api
+        from ._capi import IcpOutputs, IcpParams, IcpResult
+        ctx = self.ctx
+        p = IcpParams(float(max_correspondence_distance), float(transformation_epsilon), float(euclidean_fitness_epsilon),
+                      int(max_iterations), int(mode), 1, int(dump_iteration))
+        r, o, out = IcpResult(), IcpOutputs(), {}
+        if dump_iteration >= 0:
+            out["corr_index"] = np.empty(src_shard.n, dtype=np.int32)
+            out["corr_dist2"] = np.empty(src_shard.n, dtype=np.float32)
+            o.corr_index, o.corr_dist2 = out["corr_index"].ctypes.data, out["corr_dist2"].ctypes.data
+        parts = (C.c_double * 2)()
+        self.dist.barrier()  # nobody may still be reading the previous alignment's sums
+        ctx._check(ctx._lib.lc3d_icp_align_sharded(ctx._h, src_shard._h, tgt._h, C.byref(p), C.byref(r), C.byref(o), parts),
+                   "lc3d_icp_align_sharded")
+        out.update(api._result_dict(r))
+        allparts = [None] * self.world
+        self.dist.all_gather_object(allparts, (parts[0], parts[1]))
+        tot, cnt = sum(a for a, _ in allparts), sum(b for _, b in allparts)
+        out["fitness"] = tot / cnt if cnt > 0 else float(np.finfo(np.float64).max)
+        return out
+
+    def close(self):
+        self.ctx._lib.lc3d_shard_close(self.ctx._h)

@@ -190,7 +190,7 @@ struct IcpHooks {
 };
 void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, const lc3d_icp_params* p,
              lc3d_icp_result* res, const lc3d_icp_outputs* out, const IcpHooks& hooks = IcpHooks(),
-             bool overlap_download = false) {
+             bool overlap_download = false, bool sharded = false, double* fitness_parts = nullptr) {
   const std::function<void()>& before_source = hooks.before_source;
   cudaStream_t st = ctx->stream;
   const int n = (int)src->n;
@@ -314,8 +314,50 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   int* h_done = ctx->pinned[1].as<int>();
   cudaEvent_t chunk_ev[2] = {ctx->chunk.a, ctx->chunk.b};
   const bool pdl = !(std::getenv("LC3D_PDL") && std::atoi(std::getenv("LC3D_PDL")) == 0);
+  // source-sharded mode: partial rows go to the IPC-exported exchange buffer (double-buffered by
+  // iteration parity) and the solve kernel reads every rank's rows over peer memory
+  ShardView sv{};
+  ShardHeader* shard_hdr = nullptr;
+  double* shard_rows = nullptr;
+  if (sharded) {
+    auto& sh = ctx->shard;
+    if (sh.rank < 0 || sh.world < 1) throw CudaError{"lc3d_icp_align_sharded: call lc3d_shard_export / lc3d_shard_connect first"};
+    if (nblk > sh.row_stride) throw CudaError{"lc3d_icp_align_sharded: source shard larger than the exported capacity"};
+    if (p->max_iterations >= 65535) throw CudaError{"lc3d_icp_align_sharded: max_iterations must be < 65535"};
+    shard_hdr = reinterpret_cast<ShardHeader*>(sh.xbuf.p);
+    shard_rows = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sh.xbuf.p) + 256);
+    sh.epoch += 1;
+    sv.world = sh.world;
+    sv.rank = sh.rank;
+    sv.base = sh.epoch << 16;
+    sv.row_stride = sh.row_stride;
+    for (int r = 0; r < sh.world; ++r) {
+      unsigned char* base = reinterpret_cast<unsigned char*>(r == sh.rank ? sh.xbuf.p : sh.peer[r]);
+      sv.hdr[r] = reinterpret_cast<const ShardHeader*>(base);
+      sv.rows[r] = reinterpret_cast<const double*>(base + 256);
+    }
+  }
   auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
+    if (sharded) {
+      // this rank's rows of parity q = it & 1 start at q * 32 * row_stride; inside that region they
+      // are value-major with the pitch the search kernel writes (its grid size, published as nblk)
+      double* rows_q = shard_rows + (size_t)(it & 1) * 32 * sv.row_stride;
+      if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, rows_q, d_dump_idx, d_dump_d2);
+        LC3D_LAUNCH_PDL(ctx, pdl, shard_publish_kernel, 1, 32, d_state, shard_hdr, (unsigned)nblk, sv.base);
+        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_sharded_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state,
+                        cfg, sv, reduced);
+      } else {
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, d_state,
+                        cfg, G.v, X, Bnd, Mj, n, rows_q, d_dump_idx, d_dump_d2);
+        LC3D_LAUNCH_PDL(ctx, pdl, shard_publish_kernel, 1, 32, d_state, shard_hdr, (unsigned)nblk, sv.base);
+        LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_sharded_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
+                        sv, reduced);
+      }
+      return;
+    }
     // programmatic dependent launch: each kernel of the chain is staged while its predecessor
     // drains (the kernels call pdl_wait() before reading anything the predecessor wrote)
     if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
@@ -447,6 +489,11 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   if (p->compute_fitness)
     res->fitness = h_state->fitness_cnt > 0 ? h_state->fitness_sum / (double)h_state->fitness_cnt
                                             : std::numeric_limits<double>::max();
+  if (fitness_parts) {
+    fitness_parts[0] = p->compute_fitness ? h_state->fitness_sum : 0.0;
+    fitness_parts[1] = p->compute_fitness ? (double)h_state->fitness_cnt : 0.0;
+  }
+  if (sharded && h_state->pad[0]) throw CudaError{"lc3d_icp_align_sharded: timed out waiting for a peer's partial sums"};
   res->ms_index = ctx->tm[1].ms();
   res->ms_loop = ctx->tm[2].ms();
   res->ms_fitness = ctx->tm[3].ms();
@@ -541,6 +588,7 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   ctx->tmp_a.release();
   ctx->tmp_b.release();
   ctx->pool.release_all();
+  lc3d_shard_close(ctx);
   if (ctx->grid) {
     ctx->grid->release();
     delete ctx->grid;
@@ -681,6 +729,67 @@ int lc3d_icp_align_resident(lc3d_ctx* ctx, const lc3d_dcloud* source, const lc3d
     std::memset(result, 0, sizeof *result);
     ctx->tm[5].start(ctx->stream);
     icp_run(ctx, source, target, params, result, outputs);
+  });
+}
+
+int lc3d_shard_export(lc3d_ctx* ctx, int64_t max_shard_points, unsigned char handle_out[64]) {
+  if (!handle_out || max_shard_points <= 0) return invalid(ctx, "lc3d_shard_export: bad argument");
+  return guarded(ctx, [&] {
+    auto& sh = ctx->shard;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    sh.row_stride = div_up(max_shard_points, kIcpThreads) + 1;
+    const size_t bytes = 256 + (size_t)2 * 32 * sh.row_stride * 8;
+    if (sh.xbuf.p) sh.xbuf.release();
+    // a dedicated allocation: IPC exports whole cudaMalloc allocations
+    LC3D_CUDA(cudaMalloc(&sh.xbuf.p, bytes));
+    sh.xbuf.cap = bytes;
+    LC3D_CUDA(cudaMemset(sh.xbuf.p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    LC3D_CUDA(cudaIpcGetMemHandle(&h, sh.xbuf.p));
+    std::memcpy(handle_out, &h, 64);
+    sh.epoch = 0;
+  });
+}
+
+int lc3d_shard_connect(lc3d_ctx* ctx, int32_t rank, int32_t world, const unsigned char* handles) {
+  if (!handles || world < 1 || world > kShardMaxWorld || rank < 0 || rank >= world)
+    return invalid(ctx, "lc3d_shard_connect: bad rank / world (at most 8 ranks) or NULL handles");
+  return guarded(ctx, [&] {
+    auto& sh = ctx->shard;
+    if (!sh.xbuf.p) throw CudaError{"lc3d_shard_connect: call lc3d_shard_export first"};
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + (size_t)r * 64, 64);
+      LC3D_CUDA(cudaIpcOpenMemHandle(&sh.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    sh.rank = rank;
+    sh.world = world;
+  });
+}
+
+void lc3d_shard_close(lc3d_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  auto& sh = ctx->shard;
+  for (int r = 0; r < kShardMaxWorld; ++r)
+    if (sh.peer[r]) {
+      cudaIpcCloseMemHandle(sh.peer[r]);
+      sh.peer[r] = nullptr;
+    }
+  sh.xbuf.release();
+  sh.rank = -1;
+  sh.world = 0;
+}
+
+int lc3d_icp_align_sharded(lc3d_ctx* ctx, const lc3d_dcloud* source_shard, const lc3d_dcloud* target,
+                           const lc3d_icp_params* params, lc3d_icp_result* result, const lc3d_icp_outputs* outputs,
+                           double fitness_sum_count[2]) {
+  if (!source_shard || !target || !params || !result) return invalid(ctx, "lc3d_icp_align_sharded: NULL argument");
+  return guarded(ctx, [&] {
+    std::memset(result, 0, sizeof *result);
+    ctx->tm[5].start(ctx->stream);
+    icp_run(ctx, source_shard, target, params, result, outputs, IcpHooks(), false, true, fitness_sum_count);
   });
 }
 

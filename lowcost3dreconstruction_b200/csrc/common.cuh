@@ -225,6 +225,14 @@ struct lc3d_ctx {
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
   lc3d::BufPool pool;          // parked buffers of freed resident clouds
+  // source-sharded single-pair mode (lc3d_shard_*): exchange buffer + the peers' mappings
+  struct Shard {
+    int rank = -1, world = 0;
+    lc3d::DevBuf xbuf;          // [header 256 B][2 x 32 x row_stride doubles], exported with CUDA IPC
+    long long row_stride = 0;
+    void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // mapped peer buffers
+    unsigned epoch = 0;         // alignments run so far (the same on every rank: the calls are collective)
+  } shard;
 };
 
 namespace lc3d {

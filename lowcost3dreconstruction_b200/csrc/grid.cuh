@@ -29,7 +29,20 @@ constexpr int kCoarse = 1 << kCoarseShift;
 constexpr float kCellSlack = 1e-3f;  // cells; covers float rounding of cell coordinates
 constexpr int kMaxDim = 2048;
 constexpr int kMaxDimX = 4096;  // x-subcells
-constexpr int64_t kMaxCells = (int64_t)1 << 26;
+// Cap of the dense cell table.  A surface cloud occupies a vanishing fraction of its bounding
+// volume, so the table (4 B per cell) grows with extent^3 while the points grow with extent^2: the
+// cap is what keeps x-subdivided millimetre cells affordable.  Default 2^26 cells (256 MB of the
+// 180 GB), raised for multi-million-point clouds up to 2^29 (2 GB) so that they keep the cell edge
+// and x subdivision the search is tuned for instead of a coarser grid; LC3D_MAX_CELLS_LOG2 overrides.
+inline int64_t max_cells_for(int64_t n) {
+  if (const char* e = std::getenv("LC3D_MAX_CELLS_LOG2")) {
+    const int b = std::atoi(e);
+    if (b >= 16 && b <= 30) return (int64_t)1 << b;
+  }
+  int64_t cap = (int64_t)1 << 26;
+  while (cap < ((int64_t)1 << 29) && cap < 48 * n) cap <<= 1;
+  return cap;
+}
 
 struct GridDev {
   float ox, oy, oz;
@@ -420,6 +433,7 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
     xs *= 2;
     ++xs_shift;
   }
+  const int64_t kMaxCells = max_cells_for(n64);
   for (int iter = 0; iter < 64; ++iter) {
     int64_t tot = 1;
     for (int d = 0; d < 3; ++d) {

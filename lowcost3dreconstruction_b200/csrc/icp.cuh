@@ -74,6 +74,7 @@ __global__ void icp_state_init(IcpState* st) {
     st->state = LC3D_STATE_NOT_CONVERGED;
     st->ticket = 0;
     st->ticket2 = 0;
+    st->pad[0] = st->pad[1] = 0;
   }
 }
 
@@ -843,6 +844,115 @@ __global__ void __launch_bounds__(256)
     *queue_count = 0;
     st->fitness_sum = red[0];
     st->fitness_cnt = (long long)red[1];
+  }
+}
+
+// ---- one pair sharded by SOURCE points over the GPUs of a box (second mode) --------
+// Every rank holds the whole target + index and a slice of the source.  Per iteration each
+// rank's search kernel writes its partial estimator rows into an exchange buffer that the other
+// ranks have mapped (CUDA IPC, peer access over NVLink / NVSwitch) and publishes them with an
+// iteration stamp; the solve kernel of EVERY rank then reads all ranks' rows straight from
+// peer memory, adds them in rank order and solves — bit-identical pose and convergence decision on
+// all ranks, no separate all-reduce, no broadcast.  Rows are double-buffered by iteration parity:
+// a rank can only overwrite buffer p two iterations later, after every peer has published the
+// iteration in between, i.e. finished reading.
+constexpr int kShardMaxWorld = 8;
+struct ShardHeader {
+  unsigned stamp;   // iterations published so far (k + 1 after the rows of iteration k are complete)
+  unsigned nblk;    // partial rows per value of this rank
+  unsigned pad[2];
+};
+struct ShardView {
+  int world, rank;
+  unsigned base;                           // epoch stamp offset of this alignment (same on all ranks)
+  const ShardHeader* hdr[kShardMaxWorld];  // peers' headers (own entry included)
+  const double* rows[kShardMaxWorld];      // peers' row buffers: 2 parities x 32 values x row_stride doubles
+  long long row_stride;                    // row capacity per value (same on all ranks); rows are packed with pitch nblk
+};
+
+// stream-ordered after the search kernel: its rows are complete and visible
+__global__ void shard_publish_kernel(const IcpState* __restrict__ st, ShardHeader* hdr, unsigned nblk, unsigned base) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x != 0 || st->done) return;
+  hdr->nblk = nblk;
+  __threadfence_system();
+  *(volatile unsigned*)&hdr->stamp = base + (unsigned)st->iter + 1u;
+  __threadfence_system();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kSolveThreads)
+    icp_solve_sharded_kernel(IcpState* __restrict__ st, const IcpConfig cfg, const ShardView sv,
+                             double* __restrict__ reduced) {
+  constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  __shared__ double sm[kSolveThreads / 32];
+  __shared__ unsigned s_ticket;
+  __shared__ int s_fail;
+  pdl_wait();
+  pdl_trigger();
+  if (st->done) return;
+  const int iter = st->iter;
+  const int v = blockIdx.x;
+  // wait until every rank has published this iteration's rows (system-scope polling over peer memory)
+  if (threadIdx.x == 0) {
+    s_fail = 0;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < sv.world; ++r) {
+      while (*(volatile const unsigned*)&sv.hdr[r]->stamp < sv.base + (unsigned)iter + 1u) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) {  // 20 s: a peer died
+          s_fail = 1;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const bool fail = s_fail != 0;
+  double total = 0.0;
+  if (!fail) {
+    for (int r = 0; r < sv.world; ++r) {  // rank order: the same arithmetic on every rank
+      const int nrows = (int)*(volatile const unsigned*)&sv.hdr[r]->nblk;
+      const double* row = sv.rows[r] + (size_t)(iter & 1) * 32 * sv.row_stride + (size_t)v * nrows;
+      double s = 0.0;
+      for (int i = threadIdx.x; i < nrows; i += kSolveThreads) s += *(volatile const double*)(row + i);
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        double t = threadIdx.x < kSolveThreads / 32 ? sm[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) total += t;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    reduced[v] = total;
+    __threadfence();
+    s_ticket = atomicAdd(&st->ticket, 1u);
+  }
+  __syncthreads();
+  if (s_ticket != (unsigned)(NV - 1)) return;
+  if (threadIdx.x < 32) {
+    __threadfence();
+    const double mine = threadIdx.x < NV ? __ldcg(reduced + threadIdx.x) : 0.0;
+    double red[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[k] = __shfl_sync(0xffffffffu, mine, k);
+    if (threadIdx.x == 0) st->ticket = 0;
+    if (fail) {
+      if (threadIdx.x == 0) {
+        st->pad[0] = 1;  // exchange timed out
+        st->converged = 0;
+        st->done = 1;
+      }
+    } else {
+      icp_solve_and_test<MODE>(st, cfg, red);
+    }
   }
 }
 
