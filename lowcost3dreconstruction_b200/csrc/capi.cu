@@ -283,6 +283,13 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     for (int it = 0; it <= p->max_iterations; ++it)
       LC3D_CUDA(cudaMemsetAsync(&cfg.stats[it].c[11], 0xff, 8, st));
   }
+  unsigned long long* d_block_log = nullptr;
+  const char* block_log_path = want_stats ? std::getenv("LC3D_BLOCK_LOG") : nullptr;
+  if (block_log_path) {
+    LC3D_CUDA(cudaMalloc(&d_block_log, (size_t)p->max_iterations * nblk * 24));
+    LC3D_CUDA(cudaMemset(d_block_log, 0, (size_t)p->max_iterations * nblk * 24));
+    LC3D_CUDA(cudaMemcpyToSymbol(g_block_log, &d_block_log, sizeof(d_block_log)));
+  }
   int32_t* d_dump_idx = nullptr;
   float* d_dump_d2 = nullptr;
   const bool dump = out && (out->corr_index || out->corr_dist2) && p->dump_iteration >= 0 && n > 0;
@@ -337,6 +344,10 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
       sv.rows[r] = reinterpret_cast<const double*>(base + 256);
     }
   }
+  int ring_lo = 1, ring_hi = 2;  // LC3D_RING_ITERS=lo-hi (e.g. "1-2"; "1-0" switches the ring walk off)
+  if (const char* e = std::getenv("LC3D_RING_ITERS")) {
+    if (std::sscanf(e, "%d-%d", &ring_lo, &ring_hi) != 2) ring_lo = 1, ring_hi = 2;
+  }
   auto launch_one = [&](int it) {
     if (want_stats && it > 0) LC3D_CUDA(cudaEventRecord(iter_ev[it], st));
     if (sharded) {
@@ -360,25 +371,34 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     }
     // programmatic dependent launch: each kernel of the chain is staged while its predecessor
     // drains (the kernels call pdl_wait() before reading anything the predecessor wrote)
+    // iterations ring_lo..ring_hi (the ones right after the large first pose updates, when the
+    // previous matches are stale seeds and the search balls several cells wide) walk centre-out
+    const bool rings = it >= ring_lo && it <= ring_hi;
+#define LC3D_ITER_LAUNCH(MODE_, STATS_, RINGS_)                                                              \
+  LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<MODE_, STATS_, RINGS_>), nblk, kIcpThreads, d_state, cfg, G.v, \
+                  X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2)
     if (p->mode == LC3D_ICP_POINT_TO_PLANE) {
-      if (want_stats)
-        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, true>), nblk, kIcpThreads, d_state,
-                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
-      else
-        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false>), nblk, kIcpThreads, d_state,
-                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      if (want_stats) {
+        if (rings) LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_PLANE, true, true);
+        else LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_PLANE, true, false);
+      } else {
+        if (rings) LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_PLANE, false, true);
+        else LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_PLANE, false, false);
+      }
       LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
                       partials, nblk, reduced);
     } else {
-      if (want_stats)
-        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, true>), nblk, kIcpThreads, d_state,
-                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
-      else
-        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_POINT, false>), nblk, kIcpThreads, d_state,
-                        cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      if (want_stats) {
+        if (rings) LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_POINT, true, true);
+        else LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_POINT, true, false);
+      } else {
+        if (rings) LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_POINT, false, true);
+        else LC3D_ITER_LAUNCH(LC3D_ICP_POINT_TO_POINT, false, false);
+      }
       LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_POINT>, kNvP2P, kSolveThreads, d_state, cfg,
                       partials, nblk, reduced);
     }
+#undef LC3D_ITER_LAUNCH
   };
   {
     int it = 0, chunk = 0;
@@ -455,6 +475,19 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   ctx->tm[5].stop(st);
   LC3D_CUDA(cudaStreamSynchronize(st));
   if (ds != st) LC3D_CUDA(cudaStreamSynchronize(ds));
+  if (d_block_log) {
+    std::vector<unsigned long long> hb((size_t)p->max_iterations * nblk * 3);
+    LC3D_CUDA(cudaMemcpy(hb.data(), d_block_log, hb.size() * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = std::fopen(block_log_path, "wb")) {
+      const int hdr[2] = {p->max_iterations, nblk};
+      std::fwrite(hdr, 4, 2, f);
+      std::fwrite(hb.data(), 8, hb.size(), f);
+      std::fclose(f);
+    }
+    unsigned long long* null_log = nullptr;
+    LC3D_CUDA(cudaMemcpyToSymbol(g_block_log, &null_log, sizeof(null_log)));
+    cudaFree(d_block_log);
+  }
   if (want_stats) {
     std::vector<SearchStats> hs(p->max_iterations + 1);
     LC3D_CUDA(cudaMemcpy(hs.data(), cfg.stats, sizeof(SearchStats) * (p->max_iterations + 1), cudaMemcpyDeviceToHost));

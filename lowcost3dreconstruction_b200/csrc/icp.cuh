@@ -44,6 +44,9 @@ struct IcpState {
   int pad[2];
 };
 
+// LC3D_STATS=1 + LC3D_BLOCK_LOG=<file>: per-block (start ns, end ns, SM id) of every iteration kernel
+__device__ unsigned long long* g_block_log = nullptr;
+
 struct IcpConfig {
   float gate;         // largest float <= max_correspondence_distance^2
   float gate_ext;     // (gate_dist + margin)^2: searches run against this extended gate
@@ -506,7 +509,9 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
 #ifndef LC3D_ICP_MINBLOCKS
 #define LC3D_ICP_MINBLOCKS 8
 #endif
-template <int MODE, bool STATS>
+// RINGS: centre-out ball walk (search.cuh), chosen by the host for the iterations right after the
+// large first pose updates.
+template <int MODE, bool STATS, bool RINGS = false>
 __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
     icp_iteration_kernel(IcpState* __restrict__ st, const __grid_constant__ IcpConfig cfg,
                          const __grid_constant__ GridDev g,
@@ -536,6 +541,7 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     atomicMin(&stats->c[11], t0);
+    if (g_block_log) g_block_log[((size_t)iter * gridDim.x + blockIdx.x) * 3] = t0;
   }
   double acc = 0.0;  // lane L: total of estimator value L
   {
@@ -579,7 +585,7 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
       }
     }
 #endif
-    const Best b = nn_search_seeded(g, active && !skip, q.x, q.y, q.z, cfg.gate_ext, seed_j, stats);
+    const Best b = nn_search_seeded<false, RINGS>(g, active && !skip, q.x, q.y, q.z, cfg.gate_ext, seed_j, stats);
     const bool found = active && !skip && b.j >= 0;
     const bool has = found && b.d2 <= cfg.gate;
     if (active && !skip) {
@@ -641,6 +647,15 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   if (lane == 0) ticket = atomicAdd(&s_arrived, 1u);
   ticket = __shfl_sync(0xffffffffu, ticket, 0);
   if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
+    if (STATS && g_block_log && lane == 0) {
+      unsigned long long t1;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* rec = g_block_log + ((size_t)iter * gridDim.x + blockIdx.x) * 3;
+      rec[1] = t1;
+      rec[2] = smid;
+    }
     __threadfence_block();
     if (lane < NV) {
       double s = 0.0;
@@ -668,6 +683,9 @@ __global__ void __launch_bounds__(kSolveThreads)
   pdl_wait();     // the search kernel's partial rows
   pdl_trigger();  // the next search kernel may stage its blocks behind this one
   if (st->done) return;
+  SearchStats* stats = cfg.stats ? cfg.stats + st->iter : nullptr;  // LC3D_STATS=1 timeline
+  unsigned long long tm0 = 0, tm1 = 0, tm2 = 0;
+  if (stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
   const int v = blockIdx.x;
   const double* row = partials + (size_t)v * nwarps;
   // fixed assignment and order (deterministic); 8 independent loads in flight per thread
@@ -705,7 +723,16 @@ __global__ void __launch_bounds__(kSolveThreads)
 #pragma unroll
     for (int k = 0; k < NV; ++k) red[k] = __shfl_sync(0xffffffffu, mine, k);
     if (threadIdx.x == 0) st->ticket = 0;
+    if (stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
     icp_solve_and_test<MODE>(st, cfg, red);
+    if (stats) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm2));
+      if (threadIdx.x == 0) {
+        stats->c[8] = tm0 - stats->c[11];  // search kernel start -> start of the last solve block
+        stats->c[9] = tm1 - tm0;           // row reduce + ticket
+        stats->c[10] = tm2 - tm1;          // solve + pose composition + criteria
+      }
+    }
   }
 }
 

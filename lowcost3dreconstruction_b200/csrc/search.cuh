@@ -336,6 +336,66 @@ __device__ __forceinline__ void ball_walk(const GridDev& g, bool act, const Quer
   }
 }
 
+// Centre-out variant of the ball walk: the rows are visited ring by ring (Chebyshev rings of
+// (y,z) cells around the query's own cell).  The centre rows shrink the bound first, so that the
+// outer rings of a wide ball (stale seeds right after a large pose update) are culled by the slab
+// test instead of being scanned with the initial radius, and the loop stops as soon as no lane's
+// ball reaches the next ring (warp vote).  Pays off while the balls are several cells wide
+// (iterations 1-2 of a 5-degree pair: 152 -> 132 us and 120 -> 91 us); in the converged regime
+// (one-cell balls) the ring bookkeeping costs ~5 us per iteration, so the caller picks the walk
+// per iteration (profiles/r02_summary.md).
+__device__ __forceinline__ void ball_walk_rings(const GridDev& g, bool act, const QueryCell& qc, float qx,
+                                                float qy, float qz, Best& b, unsigned* n_cand,
+                                                unsigned* n_rows) {
+  const unsigned full = 0xffffffffu;
+  const float inv_c2 = 1.0f / (g.c * g.c * 0.9999f);
+  int W = act ? ball_halfwidth(g, b.d2) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) W = max(W, __shfl_xor_sync(full, W, o));
+  // distance (cells) from the query to the nearest face of its own (y,z) cell: every row of
+  // ring r is at least r - 1 + m cells away
+  const float m = fminf(fminf(qc.fy - (float)qc.iy, (float)(qc.iy + 1) - qc.fy),
+                        fminf(qc.fz - (float)qc.iz, (float)(qc.iz + 1) - qc.fz));
+  for (int r = 0; r <= W; ++r) {
+    if (r >= 1) {
+      const float gr = fmaxf((float)(r - 1) + m - kCellSlack, 0.0f);
+      if (!__any_sync(full, act && gr * gr <= b.d2 * inv_c2)) break;
+    }
+    const int nside = r == 0 ? 1 : 4, len = r == 0 ? 1 : 2 * r;
+    for (int side = 0; side < nside; ++side) {
+      for (int k = 0; k < len; ++k) {
+        // four sides of 2r cells each, walked around the ring
+        int dy, dz;
+        if (side == 0) { dy = k - r; dz = -r; }
+        else if (side == 1) { dy = r; dz = k - r; }
+        else if (side == 2) { dy = r - k; dz = r; }
+        else { dy = -r; dz = r - k; }
+        if (r == 0) dy = dz = 0;
+        const int yy = qc.iy + dy, zz = qc.iz + dz;
+        uint32_t s = 0, e = 0;
+        if (act && (unsigned)zz < (unsigned)g.dz && (unsigned)yy < (unsigned)g.dy) {
+          const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
+          const float rem = b.d2 * inv_c2 - (gy * gy + gz * gz);
+          if (rem >= 0.0f) {
+            const float wx = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
+            const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
+            if (xa <= xb) {
+              const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+              s = __ldg(row + xa);
+              e = __ldg(row + xb + 1);
+            }
+          }
+        }
+        if (n_rows) {
+          *n_rows += 1;
+          *n_cand += e - s;
+        }
+        for (uint32_t j = s; j < e; ++j) consider(__ldg(&g.pts[j]), (int)j, qx, qy, qz, b);
+      }
+    }
+  }
+}
+
 // Exact gated 1-NN for one query per thread, seeded.  All 32 lanes must call.
 // seed_j: position (sorted target order) of a plausible neighbour, e.g. the previous
 // iteration's match, or -1.  gate may be +inf (unbounded): lanes whose ball is too large for
@@ -360,7 +420,7 @@ constexpr int kCoopW = LC3D_COOP_W;          // balls wider than this many cells
 // pair (same-box A/B, profiles/r02_summary.md: 0 -> 0.73 ms loop, 3 -> 0.75, 6 -> 0.80, 12 -> 0.90)
 constexpr int kCoopLanes = LC3D_COOP_LANES;
 constexpr int kDeferW = LC3D_DEFER_W;
-template <bool DEFER = false>
+template <bool DEFER = false, bool RINGS = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, float qx, float qy,
                                                  float qz, float gate, int seed_j, SearchStats* stats,
                                                  bool* deferred = nullptr) {
@@ -420,8 +480,12 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, bool active, 
   }
   const bool walk = need && (Wl <= wmax || (b.j < 0 && Wl <= kBallMaxW));
   unsigned n_cand = 0, n_rows = 0;
-  if (__any_sync(full, walk))
-    ball_walk(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
+  if (__any_sync(full, walk)) {
+    if (RINGS)
+      ball_walk_rings(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
+    else
+      ball_walk(g, walk, qc, qx, qy, qz, b, stats ? &n_cand : nullptr, stats ? &n_rows : nullptr);
+  }
   if (walk) need = false;
   if (DEFER) *deferred = need;
   unsigned todo = DEFER ? 0u : __ballot_sync(full, need);
