@@ -1,5 +1,6 @@
 // capi.cu — the C ABI of include/lc3d.h over the CUDA kernels.  No CPU fallback.
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <functional>
 #include <limits>
@@ -171,10 +172,26 @@ int xsub_env() {
   int x = e ? std::atoi(e) : 8;
   return x >= 1 && x <= 16 ? x : 8;
 }
-double knn_cell_factor_env() {
-  const char* e = std::getenv("LC3D_KNN_CELL_FACTOR");
-  double f = e ? std::atof(e) : 1.5;
-  return f > 0.1 ? f : 1.5;
+// k-NN passes: the cell edge (in point spacings) is chosen from k so that the guaranteed ball of the
+// (2K+1)^3 block with K = 2 holds about kKnnFill * k points of a surface sampled at the estimated
+// spacing (pi (K cf)^2 >= fill k): 25 cell rows = one lane-parallel step of the search, one sort, and
+// a second, larger block only where the cloud is locally sparser.  LC3D_KNN_CELL_FACTOR overrides.
+constexpr double kKnnFill = 1.4;
+double knn_cell_factor(int k) {
+  if (const char* e = std::getenv("LC3D_KNN_CELL_FACTOR")) {
+    const double f = std::atof(e);
+    if (f > 0.1) return f;
+  }
+  double fill = kKnnFill;
+  if (const char* e = std::getenv("LC3D_KNN_FILL")) fill = std::max(0.5, std::atof(e));
+  const double f = std::sqrt(fill * std::max(k, 1) / 3.14159265358979) / 2.0;
+  return std::min(std::max(f, 1.0), 6.0);
+}
+// first block half-width (cells) for k neighbours on an index built with cell factor cf
+int knn_kfirst(double cf, int k) {
+  double fill = kKnnFill;
+  if (const char* e = std::getenv("LC3D_KNN_FILL")) fill = std::max(0.5, std::atof(e));
+  return std::max(1, (int)std::ceil(std::sqrt(fill * std::max(k, 1) / 3.14159265358979) / cf - 1e-3));
 }
 
 // before_source: called after the target index is built and before the source is first touched

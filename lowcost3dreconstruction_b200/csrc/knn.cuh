@@ -5,13 +5,19 @@
 //   * pcl::NormalEstimation (normal_estimation.cpp:84-108): float32 single-pass
 //     covariance -> closed-form smallest eigenpair (pcl::eigen33) -> viewpoint flip.
 //
-// Search: the warp walks Chebyshev rings of cells around the query (x-runs of cells are
-// contiguous point ranges), lanes stride over the points of a run, candidates whose key
-// (d2 bits << 32 | original index) beats the running k-th key are appended to a per-warp
-// shared-memory buffer with ballot/popc; when the buffer fills, and after every ring, it
-// is bitonic-sorted and truncated to k.  The search stops when the k-th distance is within
-// the guaranteed radius of the scanned block, which makes the result exact; order is
-// ascending (d2, index) — the order PCL's consumers sum in.
+// Search: the warp takes the (2K+1)^3 block of cells around the query and its GUARANTEED ball
+// (radius = distance from the query to the nearest block face that still has grid behind it:
+// every indexed point inside that ball lies inside the block).  The (2K+1)^2 cell rows are
+// located by the lanes in parallel (one row per lane: slab test against the ball, x-run clipped
+// to the ball, the two cell_start loads), a warp scan turns the run lengths into offsets, and
+// the candidates are then evaluated 32 at a time whatever row they come from (each lane finds
+// its run with a 5-step shuffle search).  Only points INSIDE the guaranteed ball are kept
+// (ballot/popc append to a per-warp shared-memory buffer): if there are at least k of them, the
+// k smallest keys (d2 bits << 32 | original index) are the exact k nearest neighbours and ONE
+// bitonic sort of the buffer yields them in ascending (d2, index) order — the order PCL's
+// consumers sum in.  Otherwise the block grows (by the density it has just seen) and the search
+// starts over.  The index cell edge is chosen from k (knn_cell_factor) so that K = 2 holds
+// ~1.4 k points in the ball: 25 rows = one lane-parallel step, one sort, no second ring.
 #pragma once
 #include "search.cuh"
 
@@ -20,12 +26,12 @@ namespace lc3d {
 constexpr int kKnnWarps = 4;  // warps (= queries in flight) per block
 constexpr unsigned long long kMaxKey = 0xffffffffffffffffull;
 
-template <int CAP>
+template <int N>
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* buf, int lane) {
-  for (int kk = 2; kk <= CAP; kk <<= 1) {
+  for (int kk = 2; kk <= N; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
 #pragma unroll
-      for (int t = lane; t < CAP / 2; t += 32) {
+      for (int t = lane; t < N / 2; t += 32) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const int l = i | j;
         const bool asc = (i & kk) == 0;
@@ -48,87 +54,42 @@ struct KnnState {
   int k;
 };
 
+// Sorts the buffer ascending (padded to the next power of two >= cnt, at least 32) and keeps
+// the k smallest keys.
 template <int CAP>
 __device__ __forceinline__ void knn_sort_truncate(KnnState<CAP>& s, int lane) {
-  for (int t = s.cnt + lane; t < CAP; t += 32) s.buf[t] = kMaxKey;
+  const int n = s.cnt <= 32 ? 32 : s.cnt <= 64 ? 64 : s.cnt <= 128 ? 128 : s.cnt <= 256 ? 256 : 512;
+  for (int t = s.cnt + lane; t < n; t += 32) s.buf[t] = kMaxKey;
   __syncwarp();
-  warp_bitonic_sort<CAP>(s.buf, lane);
+  if (n == 32) warp_bitonic_sort<32>(s.buf, lane);
+  else if (n == 64) warp_bitonic_sort<(CAP >= 64 ? 64 : CAP)>(s.buf, lane);
+  else if (n == 128) warp_bitonic_sort<(CAP >= 128 ? 128 : CAP)>(s.buf, lane);
+  else if (n == 256) warp_bitonic_sort<(CAP >= 256 ? 256 : CAP)>(s.buf, lane);
+  else warp_bitonic_sort<CAP>(s.buf, lane);
   if (s.cnt > s.k) s.cnt = s.k;
   s.thresh = s.cnt == s.k ? s.buf[s.k - 1] : kMaxKey;
 }
 
-// Lanes stride over the points [s0, e0) of one cell run.
-template <int CAP>
-__device__ __forceinline__ void knn_scan_run(const float4* __restrict__ pts, uint32_t s0, uint32_t e0,
-                                             float qx, float qy, float qz, KnnState<CAP>& s, int lane) {
-  const unsigned lt = (1u << lane) - 1u;
-  for (uint32_t j0 = s0; j0 < e0; j0 += 32) {
-    const uint32_t j = j0 + lane;
-    bool pass = false;
-    unsigned long long key = 0;
-    if (j < e0) {
-      const float4 p = __ldg(&pts[j]);
-      const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
-      pass = key < s.thresh;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (pass) s.buf[s.cnt + __popc(m & lt)] = key;
-    s.cnt += __popc(m);
-    __syncwarp();
-    if (s.cnt > CAP - 32) knn_sort_truncate<CAP>(s, lane);
-  }
-}
-
 // Exact kNN of (qx,qy,qz); on return s.buf[0..s.cnt) holds the neighbours ascending.
-// Warp-uniform.  k <= CAP - 32.
+// Warp-uniform.  k <= CAP - 32.  kfirst: first block half-width (cells), from the index density.
 template <int CAP>
 __device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, KnnState<CAP>& s,
-                                int lane) {
+                                int lane, int kfirst) {
+  const unsigned full = 0xffffffffu;
+  const unsigned lt = (1u << lane) - 1u;
   s.cnt = 0;
   s.thresh = kMaxKey;
   if (g.n == 0) return;
-  // the ring logic below assumes cubic cells: k-NN indices are built with xsub = 1
+  // the block logic below assumes cubic cells: k-NN indices are built with xsub = 1
   const QueryCell qc = query_cell(g, qx, qy, qz);
   const float c2 = g.c * g.c * 0.9999f;
-  // first ring that touches the grid (queries may lie outside it)
-  int K = 0;
+  // first block that touches the grid (queries may lie outside it)
+  int K = kfirst;
   K = max(K, max(-qc.ix, qc.ix - (g.dx - 1)));
   K = max(K, max(-qc.iy, qc.iy - (g.dy - 1)));
   K = max(K, max(-qc.iz, qc.iz - (g.dz - 1)));
-  // with ~cell_factor^2 points per occupied cell, ring K holds ~pi K^2 cf^2 points within
-  // its guaranteed radius: jump to the first ring that can hold k (all inner rings are
-  // scanned as part of the first block)
-  int Kfirst = max(K, (int)ceilf(sqrtf((float)s.k * (1.0f / 12.0f))));
-  bool first = true;
-  for (;; ++K) {
-    if (first) K = Kfirst;
-    const float thr_d2 = __uint_as_float((unsigned)(s.thresh >> 32));  // k-th best d2 (or NaN bits)
-    const bool have_thr = s.thresh != kMaxKey;
-    const int y0 = max(qc.iy - K, 0), y1 = min(qc.iy + K, g.dy - 1);
-    const int z0 = max(qc.iz - K, 0), z1 = min(qc.iz + K, g.dz - 1);
-    const int xa = max(qc.ix - K, 0), xb = min(qc.ix + K, g.dx - 1);
-    for (int zz = z0; zz <= z1; ++zz) {
-      const float gz = slab_gap(qc.fz, zz, zz);
-      for (int yy = y0; yy <= y1; ++yy) {
-        const float gy = slab_gap(qc.fy, yy, yy);
-        if (have_thr && (gy * gy + gz * gz) * c2 > thr_d2) continue;
-        const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
-        const bool outer = first || max(abs(yy - qc.iy), abs(zz - qc.iz)) == K;
-        if (outer) {
-          if (xa <= xb) knn_scan_run<CAP>(g.pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, s, lane);
-        } else {
-          const int xl = qc.ix - K, xh = qc.ix + K;
-          if (xl >= 0 && xl < g.dx)
-            knn_scan_run<CAP>(g.pts, __ldg(row + xl), __ldg(row + xl + 1), qx, qy, qz, s, lane);
-          if (xh >= 0 && xh < g.dx)
-            knn_scan_run<CAP>(g.pts, __ldg(row + xh), __ldg(row + xh + 1), qx, qy, qz, s, lane);
-        }
-      }
-    }
-    first = false;
-    knn_sort_truncate<CAP>(s, lane);
-    // guaranteed radius of the scanned block (faces with no grid behind them bound nothing)
+  for (;;) {
+    // guaranteed radius of block K (faces with no grid behind them bound nothing)
     float gmin = 1.0e30f;
     bool open = false;
     if (qc.ix - K > 0) { gmin = fminf(gmin, qc.fx - (float)(qc.ix - K)); open = true; }
@@ -137,12 +98,82 @@ __device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, 
     if (qc.iy + K + 1 < g.dy) { gmin = fminf(gmin, (float)(qc.iy + K + 1) - qc.fy); open = true; }
     if (qc.iz - K > 0) { gmin = fminf(gmin, qc.fz - (float)(qc.iz - K)); open = true; }
     if (qc.iz + K + 1 < g.dz) { gmin = fminf(gmin, (float)(qc.iz + K + 1) - qc.fz); open = true; }
-    if (!open) break;
     gmin = fmaxf(gmin - kCellSlack, 0.0f);
-    if (s.cnt == s.k) {
-      const float kd2 = __uint_as_float((unsigned)(s.buf[s.k - 1] >> 32));
-      if (kd2 <= gmin * gmin * c2) break;
+    const float rg2 = open ? gmin * gmin * c2 : INFINITY;  // squared guaranteed radius
+    const float rgc2 = open ? gmin * gmin : INFINITY;      // the same in cells^2
+    const int side = 2 * K + 1, total = side * side;
+    const float inv_side = 1.0f / (float)side;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      // ---- one (y,z) row per lane: its point run inside the guaranteed ball
+      const int t = t0 + lane;
+      uint32_t rs = 0, rl = 0;
+      if (t < total) {
+        int rz = (int)(((float)t + 0.5f) * inv_side);
+        rz -= (rz * side > t);  // exact for any side the int range allows
+        rz += ((rz + 1) * side <= t);
+        const int yy = qc.iy + (t - rz * side) - K, zz = qc.iz + rz - K;
+        if ((unsigned)yy < (unsigned)g.dy && (unsigned)zz < (unsigned)g.dz) {
+          const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
+          const float rem = rgc2 - (gy * gy + gz * gz);
+          if (rem >= 0.0f) {
+            int xa = max(qc.ix - K, 0), xb = min(qc.ix + K, g.dx - 1);
+            if (open) {  // clip the run to the x-extent of the ball
+              const float wx = sqrtf(rem) + 2.0f * kCellSlack;
+              xa = max(xa, (int)floorf(qc.fx - wx));
+              xb = min(xb, (int)floorf(qc.fx + wx));
+            }
+            if (xa <= xb) {
+              const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+              rs = __ldg(row + xa);
+              rl = __ldg(row + xb + 1) - rs;
+            }
+          }
+        }
+      }
+      // ---- run lengths -> offsets (inclusive warp scan)
+      uint32_t inc = rl;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(full, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const uint32_t off = inc - rl;
+      const uint32_t T = __shfl_sync(full, inc, 31);
+      // ---- candidates, 32 at a time whatever their row
+      for (uint32_t base = 0; base < T; base += 32) {
+        const uint32_t c = base + lane;
+        int r = 0;  // the last run whose offset is <= c: the non-empty run that holds candidate c
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int pr = r + step;
+          const uint32_t v = __shfl_sync(full, off, pr & 31);
+          if (pr < 32 && v <= c) r = pr;
+        }
+        const uint32_t rs_r = __shfl_sync(full, rs, r), off_r = __shfl_sync(full, off, r);
+        bool pass = false;
+        unsigned long long key = 0;
+        if (c < T) {
+          const float4 p = __ldg(&g.pts[rs_r + (c - off_r)]);
+          const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+          key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+          pass = d2 <= rg2 && key < s.thresh;
+        }
+        const unsigned m = __ballot_sync(full, pass);
+        if (pass) s.buf[s.cnt + __popc(m & lt)] = key;
+        s.cnt += __popc(m);
+        __syncwarp();
+        if (s.cnt > CAP - 32) knn_sort_truncate<CAP>(s, lane);  // crowded cells: keep the best k so far
+      }
     }
+    const int found = s.cnt;  // points inside the guaranteed ball (>= k if the buffer was truncated)
+    knn_sort_truncate<CAP>(s, lane);
+    if (!open) break;              // the block covers the whole grid
+    if (s.cnt == s.k) break;       // k points inside the guaranteed ball: exact
+    // too few: grow the block by the density just seen (at least one cell) and start over
+    const float grow = sqrtf(1.3f * (float)s.k / (float)max(found, 1));
+    K = max(K + 1, min(2 * K + 1, (int)ceilf((float)K * grow)));
+    s.cnt = 0;
+    s.thresh = kMaxKey;
   }
 }
 
@@ -246,6 +277,7 @@ struct KnnArgs {
   float* out_normal;  // nq x 3   (kConsumeNormals)
   float* out_curv;    // nq
   float vpx, vpy, vpz;
+  int kfirst;  // first block half-width in cells (knn_kfirst)
 };
 
 template <int CAP, int CONSUMER>
@@ -264,7 +296,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_consta
   s.cnt = 0;
   s.thresh = kMaxKey;
   const bool ok = finite3(q.x, q.y, q.z);
-  if (ok) knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane);
+  if (ok) knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane, a.kfirst);
   __syncwarp();
   if (CONSUMER == kConsumeIndices) {
     for (int t = lane; t < a.k; t += 32) {
