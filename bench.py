@@ -43,6 +43,8 @@ WORKLOAD = ("point-to-plane ICP, 640x480 synthetic Kinect-v1 full-frame pair (~3
 CHAIN_VIEWS = 36
 CHAIN_STEP = 360.0 / CHAIN_VIEWS
 CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL = 0.002, 50, 1.0
+CHAIN_PREFETCH = int(os.environ.get("LC3D_CHAIN_PREFETCH", "1"))  # views prepared ahead on a worker thread (0 = serial)
+CHAIN_LANES = int(os.environ.get("LC3D_CHAIN_LANES", "2"))  # host threads (pair sub-blocks) per GPU
 
 
 # ------------------------------------------------------------------------------------ inputs
@@ -212,22 +214,29 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     import torch.distributed as dist
     from lowcost3dreconstruction_b200 import api, chain
 
+    # LANES host threads share the GPU, each with two contexts (own streams, own scratch): one aligns
+    # the pairs of its sub-block, the other runs the per-view passes one view ahead (chain.align_pairs)
+    n_lanes = max(1, min(CHAIN_LANES, len(pairs)))
+    icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_lanes - 1)]
+    prep_ctx = [api.Context(ctx.device) for _ in range(n_lanes)]
+    pinned = {v: api.host_register(a) for v, a in raw.items()}  # the PLY loader's buffers, pinned once
+
     def one_chain():
-        """this rank's views prepared on the device (each once), its pairs aligned resident"""
-        prepared, local, npts = {}, np.zeros((CHAIN_VIEWS - 1, chain.RECORD)), []
+        """this rank's views prepared on the device, its pairs aligned resident"""
+        local, npts = np.zeros((CHAIN_VIEWS - 1, chain.RECORD)), []
 
-        def view(v):
-            if v not in prepared:
-                prepared[v], cnt = api.prepare_view(raw[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=ctx)
+        def lane(i):
+            def get_view(v):
+                d, cnt = api.prepare_view(pinned[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=prep_ctx[i])
                 npts.append(cnt[2])
-            return prepared[v]
+                return d
 
-        for p in pairs:
-            r = api.icp_align(view(p), view(p - 1), MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=ctx)
-            local[p - 1] = chain.pack_record(r)
-            prepared.pop(p - 1).free()
-        for d in prepared.values():
-            d.free()
+            def align(src, tgt):
+                return api.icp_align(src, tgt, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=icp_ctx[i])
+
+            return get_view, align, (lambda d: d.free())
+
+        chain.align_pairs_lanes(pairs, [lane(i) for i in range(n_lanes)], local, prefetch=CHAIN_PREFETCH)
         return chain.exchange_records(local, dev), npts  # one gather per chain (20 doubles per pair)
 
     one_chain()  # warm-up: allocations, NCCL communicator
@@ -242,6 +251,10 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    for a in pinned.values():
+        api.host_unregister(a)
+    for c in prep_ctx + icp_ctx[1:]:
+        c.close()
     if rank != 0:
         return None
     dt = float(tt[0])
@@ -259,9 +272,11 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
             "median_rot_err_deg_vs_truth": float(np.median(errs)), "max_rot_err_deg_vs_truth": float(np.max(errs)),
             "points_per_view_after_voxel_sor": int(np.mean(npts)) if npts else 0,
             "pose_35_translation_m": [float(x) for x in poses[-1][:3, 3]],
-            "timed": "per view VoxelGrid 2 mm + SOR k=50 + normals k=30 on the device (lc3d_prepare_view, host xyz in), "
-                     "per pair point-to-plane ICP on the resident views, one record gather per chain; wall clock "
-                     "bracketed by barrier + cuda synchronize, max over ranks"}
+            "prefetch_views": CHAIN_PREFETCH, "lanes_per_gpu": n_lanes,
+            "timed": "per view VoxelGrid 2 mm + SOR k=50 + normals k=30 on the device (lc3d_prepare_view, page-locked host "
+                     "xyz in, on a second context one view ahead of the pair being aligned), per pair point-to-plane "
+                     "ICP on the resident views, one record gather per chain; wall clock bracketed by barrier + cuda "
+                     "synchronize, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------- main arm

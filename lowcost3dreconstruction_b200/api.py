@@ -99,6 +99,21 @@ class DeviceCloud:
             pass
 
 
+def host_register(a: np.ndarray) -> np.ndarray:
+    """Page-locks the array's buffer in place (lc3d_host_register = cudaHostRegister): uploads from
+    it are direct DMA instead of staged pageable copies.  Returns the (contiguous float32) array;
+    pair with host_unregister before the buffer is freed."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    rc = _capi.load().lc3d_host_register(C.c_void_p(a.ctypes.data), a.nbytes)
+    if rc != 0:
+        raise Lc3dError(f"lc3d_host_register failed ({rc})")
+    return a
+
+
+def host_unregister(a: np.ndarray) -> None:
+    _capi.load().lc3d_host_unregister(C.c_void_p(a.ctypes.data))
+
+
 _default_ctx: Context | None = None
 
 

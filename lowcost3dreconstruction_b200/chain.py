@@ -68,25 +68,101 @@ def exchange_records(local: np.ndarray, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+def align_pairs(pairs: Sequence[int], get_view: Callable[[int], object], align: Callable[[object, object], dict],
+                local: np.ndarray, prefetch: int = 0, release: Callable[[object], None] | None = None) -> None:
+    """Aligns `pairs` (a contiguous block, ascending) and writes their records into `local`.
+
+    prefetch = 0: everything on the calling thread, view v fetched right before its first pair.
+    prefetch > 0: get_view runs on ONE worker thread up to `prefetch` views ahead of the pair that is
+    being aligned — with get_view bound to its own lc3d context (its own stream and scratch), the
+    per-view passes (VoxelGrid, SOR, normals: short kernels separated by host round trips) overlap
+    the ICP loop of the previous pair on the same GPU (the scripts/alignment.sh:99-113 stages as a
+    two-stage software pipeline).  release(view), if given, runs on the same worker (a view's
+    buffers go back to the pool of the context that made them, which is not thread-safe)."""
+    pairs = list(pairs)
+    if not pairs:
+        return
+    views = sorted({p for p in pairs} | {p - 1 for p in pairs})
+    if prefetch <= 0:
+        cache: dict[int, object] = {}
+        for p in pairs:
+            for v in (p, p - 1):
+                if v not in cache:
+                    cache[v] = get_view(v)
+            local[p - 1] = pack_record(align(cache[p], cache[p - 1]))
+            old = cache.pop(p - 1)
+            if release:
+                release(old)
+        if release:
+            for v in cache.values():
+                release(v)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut, nxt = {}, 0
+
+        def top_up(upto):  # keep views[..upto] submitted
+            nonlocal nxt
+            while nxt < len(views) and nxt <= upto:
+                fut[views[nxt]] = pool.submit(get_view, views[nxt])
+                nxt += 1
+
+        top_up(1 + prefetch)
+        for i, p in enumerate(pairs):
+            tgt, src = fut[p - 1].result(), fut[p].result()
+            top_up(i + 2 + prefetch)  # views[i + 1] = p is in use; stay `prefetch` views ahead
+            local[p - 1] = pack_record(align(src, tgt))
+            del fut[p - 1]
+            if release:
+                pool.submit(release, tgt)
+        if release:
+            for f in fut.values():
+                pool.submit(release, f.result())
+
+
+def align_pairs_lanes(pairs: Sequence[int], lanes: Sequence[tuple], local: np.ndarray, prefetch: int = 0) -> None:
+    """Several host threads on ONE GPU: `pairs` is split into len(lanes) contiguous sub-blocks, lane i =
+    (get_view, align, release) bound to its own lc3d contexts runs align_pairs on sub-block i in its
+    own thread.  A turntable view after VoxelGrid + SOR is ~50k points: one pair keeps the 148 SMs
+    busy for a fraction of each launch, so independent pairs on independent streams fill the rest.
+    Costs len(lanes) - 1 extra view preparations (the sub-blocks' border views)."""
+    pairs = list(pairs)
+    lanes = list(lanes)[:max(1, len(pairs))]
+    if len(lanes) <= 1:
+        gv, al, rl = lanes[0]
+        return align_pairs(pairs, gv, al, local, prefetch, rl)
+    import threading
+    errors: list[BaseException] = []
+
+    def run(i):
+        try:
+            sub = shard_pairs(len(pairs), len(lanes), i)  # 1-based positions inside `pairs`
+            gv, al, rl = lanes[i]
+            align_pairs([pairs[j - 1] for j in sub], gv, al, local, prefetch, rl)
+        except BaseException as e:  # noqa: BLE001 - re-raised on the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(i,), name=f"lc3d-lane-{i}") for i in range(len(lanes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
 def register_chain(n_views: int, get_view: Callable[[int], object], align: Callable[[object, object], dict],
-                   rank: int = 0, world: int = 1, device=None) -> dict:
+                   rank: int = 0, world: int = 1, device=None, prefetch: int = 0,
+                   release: Callable[[object], None] | None = None) -> dict:
     """Registers views 1..n_views-1 pairwise (view p onto view p-1).
 
     get_view(v): returns view v's cloud (called only for the views this rank needs).
     align(source, target): returns the result dict of `api.icp_align` (or a compatible one).
+    prefetch / release: see align_pairs (views prepared ahead on a worker thread).
     Returns, on every rank: dict(pair=[records 1..], pose=[G_0..G_{n-1}])."""
     n_pairs = n_views - 1
     local = np.zeros((n_pairs, RECORD), dtype=np.float64)
-    cache: dict[int, object] = {}
-
-    def view(v):
-        if v not in cache:
-            cache[v] = get_view(v)
-        return cache[v]
-
-    for p in shard_pairs(n_pairs, world, rank):
-        local[p - 1] = pack_record(align(view(p), view(p - 1)))
-        cache.pop(p - 1, None)
+    align_pairs(shard_pairs(n_pairs, world, rank), get_view, align, local, prefetch, release)
     allrec = exchange_records(local, device)
     pairs = [unpack_record(r) for r in allrec]
     poses = compose_chain([pr["transformation"] for pr in pairs])

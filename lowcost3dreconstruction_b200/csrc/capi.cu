@@ -223,6 +223,12 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // runs on the auxiliary stream while this stream orders the source along the Morton curve of
   // the planned cells — two independent chains of short launch-bound kernels
   grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env());
+  // host-buffer point-to-plane: the target normals are still crossing PCIe — build the index and
+  // run the search of iteration 0 without them, gather them into index order afterwards and let
+  // icp_estimate_kernel compute iteration 0's sums (LC3D_DEFER_NORMALS=0 switches it off)
+  const bool defer_normals = hooks.before_target_normals && p->mode == LC3D_ICP_POINT_TO_PLANE && tgt->has_normal &&
+                             tgt->n > 0 && n > 0 && !sharded && !std::getenv("LC3D_STATS") &&
+                             !(std::getenv("LC3D_DEFER_NORMALS") && std::atoi(std::getenv("LC3D_DEFER_NORMALS")) == 0);
   const bool two_streams = ctx->aux_stream != nullptr && !std::getenv("LC3D_NO_AUX");
   {
     struct StreamSwap {
@@ -232,8 +238,9 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     } swap{ctx, ctx->stream};
     if (two_streams) ctx->stream = ctx->aux_stream;
     const float gate0 = gate_from_distance(p->max_correspondence_distance);
-    grid_fill(ctx, G, tgt->xyz.as<float4>(), tgt->has_normal ? tgt->normal.as<float4>() : nullptr, tgt->n,
-              hooks.before_target_normals,
+    grid_fill(ctx, G, tgt->xyz.as<float4>(),
+              tgt->has_normal && !defer_normals ? tgt->normal.as<float4>() : nullptr, tgt->n,
+              defer_normals ? std::function<void()>() : hooks.before_target_normals,
               std::isinf(gate0) || std::getenv("LC3D_NO_OCC") ? 0.0 : (double)std::nextafterf(std::sqrt(gate0), INFINITY));
     if (two_streams) LC3D_CUDA(cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
   }
@@ -388,6 +395,21 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
     }
     // programmatic dependent launch: each kernel of the chain is staged while its predecessor
     // drains (the kernels call pdl_wait() before reading anything the predecessor wrote)
+    if (it == 0 && defer_normals) {
+      if (ring_lo <= 0 && ring_hi >= 0)
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false, true, true>), nblk, kIcpThreads,
+                        d_state, cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      else
+        LC3D_LAUNCH_PDL(ctx, pdl, (icp_iteration_kernel<LC3D_ICP_POINT_TO_PLANE, false, false, true>), nblk, kIcpThreads,
+                        d_state, cfg, G.v, X, Bnd, Mj, n, partials, d_dump_idx, d_dump_d2);
+      hooks.before_target_normals();
+      grid_attach_normals(ctx, G, tgt->normal.as<float4>(), tgt->n);
+      LC3D_LAUNCH(ctx, icp_estimate_kernel<LC3D_ICP_POINT_TO_PLANE>, nblk, kIcpThreads, 0, d_state, cfg, G.v, X, Mj, n,
+                  partials);
+      LC3D_LAUNCH_PDL(ctx, pdl, icp_solve_kernel<LC3D_ICP_POINT_TO_PLANE>, kNvP2Plane, kSolveThreads, d_state, cfg,
+                      partials, nblk, reduced);
+      return;
+    }
     // iterations ring_lo..ring_hi (the ones right after the large first pose updates, when the
     // previous matches are stale seeds and the search balls several cells wide) walk centre-out
     const bool rings = it >= ring_lo && it <= ring_hi;

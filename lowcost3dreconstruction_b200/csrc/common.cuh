@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -148,9 +149,11 @@ namespace lc3d {
 // here and handed out again, so the steady state of a chain allocates nothing.
 struct BufPool {
   std::vector<DevBuf> free_list;
+  std::mutex mu;  // a resident cloud may be freed from another host thread than the one that made it
   static constexpr size_t kMaxParked = 32;
   // a parked buffer of at least `bytes` (and not absurdly larger), or a fresh allocation
   DevBuf acquire(size_t bytes) {
+    std::unique_lock<std::mutex> lock(mu);
     int best = -1;
     for (int i = 0; i < (int)free_list.size(); ++i)
       if (free_list[i].cap >= bytes && free_list[i].cap <= 4 * bytes + (1u << 20) &&
@@ -161,12 +164,14 @@ struct BufPool {
       b = free_list[best];
       free_list.erase(free_list.begin() + best);
     } else {
+      lock.unlock();
       b.ensure(bytes);
     }
     return b;
   }
   void park(DevBuf& b) {
     if (!b.p) return;
+    std::lock_guard<std::mutex> lock(mu);
     if (free_list.size() >= kMaxParked) {  // drop the smallest parked buffer
       int small = 0;
       for (int i = 1; i < (int)free_list.size(); ++i)
@@ -179,6 +184,7 @@ struct BufPool {
     b.cap = 0;
   }
   void release_all() {
+    std::lock_guard<std::mutex> lock(mu);
     for (auto& b : free_list) b.release();
     free_list.clear();
   }

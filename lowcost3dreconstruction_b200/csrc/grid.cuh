@@ -565,6 +565,23 @@ inline void grid_fill(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* n
   g.nrm = nrm ? G.nrm.as<float4>() : nullptr;
 }
 
+// Target normals gathered into the index order AFTER the fill (host-buffer ICP: the index is built
+// and the first search runs while the normals are still crossing PCIe).  pts[j].w = original index.
+__global__ void __launch_bounds__(256)
+    gather_normals_sorted(const float4* __restrict__ pts, const float4* __restrict__ nrm_in, int n,
+                          float4* __restrict__ nrm_sorted) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  nrm_sorted[j] = nrm_in[__float_as_int(pts[j].w)];
+}
+inline void grid_attach_normals(lc3d_ctx* ctx, Grid& G, const float4* nrm, int64_t n64) {
+  const int n = (int)n64;  // every slot of the sorted array carries its original index in w
+  if (n == 0 || G.v.n == 0) return;
+  G.nrm.ensure((size_t)n64 * 16 + 16);
+  LC3D_LAUNCH(ctx, gather_normals_sorted, div_up(n, 256), 256, 0, G.v.pts, nrm, n, G.nrm.as<float4>());
+  G.v.nrm = G.nrm.as<float4>();
+}
+
 inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
                        double cell_factor, double min_cell = 0.0, int xsub = 1) {
   grid_plan(ctx, G, xyz, n64, cell_factor, min_cell, xsub);

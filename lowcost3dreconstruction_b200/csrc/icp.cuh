@@ -493,6 +493,63 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
   return 0.0;
 }
 
+// The estimator sums of one warp (fp64): lane L returns the warp total of value L.  has: this lane
+// holds a correspondence (q = transformed source point, j = sorted-target position of its match,
+// d2 = its squared distance).  Shared by the fused iteration kernel and icp_estimate_kernel, so
+// both produce bit-identical rows.
+template <int MODE>
+__device__ __forceinline__ double icp_estimator_acc(const GridDev& g, bool has, const float4 q, int j, float d2f,
+                                                    int lane) {
+  if (!__any_sync(0xffffffffu, has)) return 0.0;
+  float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has) d = __ldg(&g.pts[j]);
+  const double d2v = has ? (double)d2f : 0.0, one = has ? 1.0 : 0.0;
+  if (MODE == LC3D_ICP_POINT_TO_PLANE) {
+    double J[6] = {0, 0, 0, 0, 0, 0}, r = 0;
+    if (has) {
+      const float4 nn = __ldg(&g.nrm[j]);
+      if (finite3(nn.x, nn.y, nn.z)) {
+        // float32 products widened to double, as TransformationEstimationPointToPlaneLLS
+        J[0] = (double)(nn.z * q.y - nn.y * q.z);
+        J[1] = (double)(nn.x * q.z - nn.z * q.x);
+        J[2] = (double)(nn.y * q.x - nn.x * q.y);
+        J[3] = nn.x;
+        J[4] = nn.y;
+        J[5] = nn.z;
+        r = (double)(nn.x * d.x + nn.y * d.y + nn.z * d.z - nn.x * q.x - nn.y * q.y - nn.z * q.z);
+      }
+    }
+    return warp_reduce_scatter32([&](int i) { return p2plane_value(i, J, r, d2v, one); }, lane);
+  }
+  const double sv[3] = {has ? (double)q.x : 0.0, has ? (double)q.y : 0.0, has ? (double)q.z : 0.0};
+  const double dv[3] = {d.x, d.y, d.z};
+  return warp_reduce_scatter32([&](int i) { return p2p_value(i, sv, dv, d2v, one); }, lane);
+}
+
+// One partial row per BLOCK (value-major) without a block barrier: every warp parks its row in
+// shared memory and retires; the LAST warp to arrive (shared-memory ticket) adds the rows in warp
+// order (fixed order: deterministic) and writes the block's row.  Warps still retire independently,
+// and the solve kernel reads 4x fewer rows.
+template <int NV>
+__device__ __forceinline__ void icp_block_row(double acc, double (*s_rows)[32], unsigned* s_arrived,
+                                              double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  s_rows[w][lane] = acc;
+  __threadfence_block();
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(s_arrived, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
+    __threadfence_block();
+    if (lane < NV) {
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += ((volatile double*)s_rows[ww])[lane];
+      partials[(size_t)lane * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
 // One ICP iteration = this kernel + icp_solve_kernel.  X: working copy of the source (float4,
 // Morton order, w = original index), transformed in place.  One thread per source point; the
 // 32 estimator sums of a warp are reduced with one butterfly reduce-scatter (lane L ends up
@@ -511,7 +568,10 @@ __device__ __forceinline__ double p2p_value(int i, const double* sv, const doubl
 #endif
 // RINGS: centre-out ball walk (search.cuh), chosen by the host for the iterations right after the
 // large first pose updates.
-template <int MODE, bool STATS, bool RINGS = false>
+// SEARCH_ONLY: correspondences only (Mj, Bnd, the dump) — the estimator sums are left to
+// icp_estimate_kernel.  The host-buffer path runs iteration 0 this way: the search needs no target
+// normals, so their upload (PCIe) hides behind the most expensive search of the alignment.
+template <int MODE, bool STATS, bool RINGS = false, bool SEARCH_ONLY = false>
 __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
     icp_iteration_kernel(IcpState* __restrict__ st, const __grid_constant__ IcpConfig cfg,
                          const __grid_constant__ GridDev g,
@@ -533,7 +593,7 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
   __syncthreads();
   if (s_flags[0]) return;
   const int iter = s_flags[1];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   // the statistics plumbing is compiled out of the production instantiation: the search
   // kernel is register-bound and every live counter costs occupancy
   SearchStats* stats = (STATS && cfg.stats) ? cfg.stats + iter : nullptr;
@@ -609,61 +669,50 @@ __global__ void __launch_bounds__(kIcpThreads, LC3D_ICP_MINBLOCKS)
       dump_idx[oi] = has ? b.oi : -1;
       dump_d2[oi] = has ? b.d2 : INFINITY;
     }
-    // ---- estimator sums, fp64 ----------------------------------------------------
-    if (__any_sync(0xffffffffu, has)) {
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has) d = __ldg(&g.pts[b.j]);
-      const double d2v = has ? (double)b.d2 : 0.0, one = has ? 1.0 : 0.0;
-      if (MODE == LC3D_ICP_POINT_TO_PLANE) {
-        double J[6] = {0, 0, 0, 0, 0, 0}, r = 0;
-        if (has) {
-          const float4 nn = __ldg(&g.nrm[b.j]);
-          if (finite3(nn.x, nn.y, nn.z)) {
-            // float32 products widened to double, as TransformationEstimationPointToPlaneLLS
-            J[0] = (double)(nn.z * q.y - nn.y * q.z);
-            J[1] = (double)(nn.x * q.z - nn.z * q.x);
-            J[2] = (double)(nn.y * q.x - nn.x * q.y);
-            J[3] = nn.x;
-            J[4] = nn.y;
-            J[5] = nn.z;
-            r = (double)(nn.x * d.x + nn.y * d.y + nn.z * d.z - nn.x * q.x - nn.y * q.y - nn.z * q.z);
-          }
-        }
-        acc += warp_reduce_scatter32([&](int i) { return p2plane_value(i, J, r, d2v, one); }, lane);
-      } else {
-        const double sv[3] = {has ? (double)q.x : 0.0, has ? (double)q.y : 0.0, has ? (double)q.z : 0.0};
-        const double dv[3] = {d.x, d.y, d.z};
-        acc += warp_reduce_scatter32([&](int i) { return p2p_value(i, sv, dv, d2v, one); }, lane);
-      }
-    }
+    if (!SEARCH_ONLY) acc = icp_estimator_acc<MODE>(g, has, q, b.j, b.d2, lane);
   }
-  // ---- one partial row per BLOCK (value-major) without a block barrier: every warp parks its
-  // row in shared memory and retires; the LAST warp to arrive (shared-memory ticket) adds the
-  // rows in warp order (fixed order: deterministic) and writes the block's row.  Warps still
-  // retire independently, and the solve kernel reads 4x fewer rows.
-  s_rows[w][lane] = acc;
-  __threadfence_block();
-  unsigned ticket = 0;
-  if (lane == 0) ticket = atomicAdd(&s_arrived, 1u);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
-    if (STATS && g_block_log && lane == 0) {
-      unsigned long long t1;
-      unsigned smid;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* rec = g_block_log + ((size_t)iter * gridDim.x + blockIdx.x) * 3;
-      rec[1] = t1;
-      rec[2] = smid;
-    }
-    __threadfence_block();
-    if (lane < NV) {
-      double s = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += ((volatile double*)s_rows[ww])[lane];
-      partials[(size_t)lane * gridDim.x + blockIdx.x] = s;
-    }
+  if (!SEARCH_ONLY) icp_block_row<NV>(acc, s_rows, &s_arrived, partials);
+  if (STATS && g_block_log && lane == 0) {  // block end = its last warp's end
+    unsigned long long t1;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* rec = g_block_log + ((size_t)iter * gridDim.x + blockIdx.x) * 3;
+    atomicMax(&rec[1], t1);
+    rec[2] = smid;
   }
+}
+
+// The estimator half of an iteration whose search ran SEARCH_ONLY (iteration 0: no transform has
+// been applied yet, X is the source as uploaded).  Same thread <-> point mapping, same arithmetic
+// (the match distance is recomputed with the expression the search used) and the same row layout as
+// the fused kernel: the partial rows are bit-identical.
+template <int MODE>
+__global__ void __launch_bounds__(kIcpThreads)
+    icp_estimate_kernel(const IcpState* __restrict__ st, const __grid_constant__ IcpConfig cfg,
+                        const __grid_constant__ GridDev g, const float4* __restrict__ X,
+                        const int* __restrict__ Mj, int n, double* __restrict__ partials) {
+  constexpr int NV = MODE == LC3D_ICP_POINT_TO_PLANE ? kNvP2Plane : kNvP2P;
+  __shared__ double s_rows[kIcpThreads / 32][32];
+  __shared__ unsigned s_arrived;
+  pdl_wait();
+  if (threadIdx.x == 0) s_arrived = 0u;
+  __syncthreads();
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  const float4 q = active ? X[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int j = active ? Mj[i] : -1;
+  bool has = false;
+  float d2 = 0.0f;
+  if (j >= 0) {
+    const float4 d = __ldg(&g.pts[j]);
+    d2 = dist2_exact(q.x, q.y, q.z, d.x, d.y, d.z);
+    has = d2 <= cfg.gate;
+  }
+  const double acc = icp_estimator_acc<MODE>(g, has, q, j, d2, lane);
+  icp_block_row<NV>(acc, s_rows, &s_arrived, partials);
 }
 
 // Second kernel of an iteration: block v reduces estimator value v over all warp rows in a

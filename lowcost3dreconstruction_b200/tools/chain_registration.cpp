@@ -15,6 +15,9 @@
 // results (lc3d_icp_align_resident): one PLY read and one PLY write per view, nothing in between.
 // The loaded views are page-locked (lc3d_host_register) because each one crosses PCIe more than
 // once (as source, as target, and for the final transform).
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "cli_common.hpp"
@@ -115,15 +118,57 @@ int main(int argc, char* argv[]) {
             res[(size_t)p].error = lc3d_last_error(ctx);
         }
       } else {
-        // views first .. first+count prepared on the device (each once), pairs on the resident results;
-        // the filtered views come back to the host for the final transform + write
-        lc3d_dcloud* prev = nullptr;
-        for (int v = first; v <= first + count; ++v) {
-          const lc3d_cloud c = as_lc3d(views[(size_t)v], false);
-          lc3d_dcloud* cur = nullptr;
+        // views first .. first+count prepared on the device (each once) by a SECOND context on its own
+        // thread, up to two views ahead of the pair being aligned: the per-view passes (short kernels
+        // separated by host round trips) overlap the ICP loop of the previous pair on the same GPU.
+        // Pairs run on the resident results; the filtered views come back to the host for the final
+        // transform + write.
+        struct Prepared {
+          lc3d_dcloud* d = nullptr;
           int64_t cnt[3] = {0, 0, 0};
           std::string err;
-          if (lc3d_prepare_view(ctx, &c, &prep, &cur, cnt) != LC3D_OK) err = lc3d_last_error(ctx);
+        };
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<Prepared> ready;
+        bool stop = false;
+        lc3d_ctx* pctx = nullptr;
+        std::string perr;
+        if (lc3d_create(dev, nullptr, &pctx) != LC3D_OK) perr = lc3d_last_error(nullptr);
+        std::thread preparer([&] {
+          for (int v = first; v <= first + count; ++v) {
+            Prepared pr;
+            if (!perr.empty()) {
+              pr.err = perr;
+            } else {
+              const lc3d_cloud c = as_lc3d(views[(size_t)v], false);
+              if (lc3d_prepare_view(pctx, &c, &prep, &pr.d, pr.cnt) != LC3D_OK) pr.err = lc3d_last_error(pctx);
+            }
+            std::unique_lock<std::mutex> lock(mu);
+            cv.wait(lock, [&] { return ready.size() < 2 || stop; });
+            if (stop) {
+              lock.unlock();
+              if (pr.d) lc3d_cloud_free(pctx, pr.d);
+              return;
+            }
+            const bool failed = !pr.err.empty();
+            ready.push_back(pr);
+            cv.notify_all();
+            if (failed) return;
+          }
+        });
+        lc3d_dcloud* prev = nullptr;
+        for (int v = first; v <= first + count; ++v) {
+          Prepared pr;
+          {
+            std::unique_lock<std::mutex> lock(mu);
+            cv.wait(lock, [&] { return !ready.empty(); });
+            pr = ready.front();
+            ready.pop_front();
+            cv.notify_all();
+          }
+          lc3d_dcloud* cur = pr.d;
+          std::string err = pr.err;
           if (err.empty() && v > first &&
               lc3d_icp_align_resident(ctx, cur, prev, &prm, &res[(size_t)v - 1].r, nullptr) != LC3D_OK)
             err = lc3d_last_error(ctx);
@@ -131,7 +176,7 @@ int main(int argc, char* argv[]) {
           // the block that registers it; shared border views are written by the block that sources them
           if (err.empty() && (v > first || v == 0)) {
             Cloud& dst = filtered[(size_t)v];
-            const size_t m = (size_t)cnt[2];
+            const size_t m = (size_t)pr.cnt[2];
             std::vector<float> xyz(3 * m + 3), nrm(3 * m + 3), curv(m + 1);
             if (m > 0 && lc3d_cloud_download(ctx, cur, xyz.data(), nrm.data(), curv.data()) != LC3D_OK)
               err = lc3d_last_error(ctx);
@@ -146,11 +191,20 @@ int main(int argc, char* argv[]) {
           }
           if (!err.empty())
             for (int p = std::max(v - 1, first); p < first + count; ++p) res[(size_t)p].error = err;
-          lc3d_cloud_free(ctx, prev);
+          if (prev) lc3d_cloud_free(pctx, prev);  // back to the pool of the context that made it (thread-safe)
           prev = cur;
           if (!err.empty()) break;
         }
-        lc3d_cloud_free(ctx, prev);
+        {
+          std::lock_guard<std::mutex> lock(mu);
+          stop = true;
+          cv.notify_all();
+        }
+        preparer.join();
+        if (prev) lc3d_cloud_free(pctx, prev);
+        for (auto& pr : ready)
+          if (pr.d) lc3d_cloud_free(pctx, pr.d);
+        if (pctx) lc3d_destroy(pctx);
       }
       lc3d_destroy(ctx);
     };

@@ -86,3 +86,39 @@ def test_gloo_world2_matches_world1():
             R = p1[k][:3, :3]
             ang = np.degrees(np.arctan2(R[2, 0], R[0, 0]))
             assert abs(ang - 4.0 * k) < 0.5 * k + 0.3, (k, ang)  # coarse 4.6k-pt views, PCL stops on rel-MSE 1e-3
+
+
+def test_align_pairs_prefetch_matches_serial():
+    """chain.align_pairs: every needed view is fetched exactly once and released exactly once, the
+    records are the same with views prepared ahead on the worker thread (prefetch 1, 2) as serially."""
+    import threading
+    import time
+
+    def run(pairs, prefetch):
+        gets, rel, threads = [], [], set()
+
+        def get_view(v):
+            time.sleep(0.002)
+            gets.append(v)
+            threads.add(threading.current_thread().name)
+            return ("view", v)
+
+        def align(s, t):
+            assert s[1] == t[1] + 1
+            time.sleep(0.002)
+            return dict(transformation=np.eye(4) * s[1], fitness=0.5 * s[1], iterations=3, converged=True, state=1)
+
+        local = np.zeros((12, chain.RECORD))
+        chain.align_pairs(pairs, get_view, align, local, prefetch=prefetch, release=lambda d: rel.append(d[1]))
+        return local, gets, rel, threads
+
+    for pairs in ([1, 2, 3, 4, 5], [4, 5, 6], [9], []):
+        ref, gets0, rel0, _ = run(pairs, 0)
+        need = sorted(set(pairs) | {p - 1 for p in pairs})
+        assert sorted(gets0) == need and sorted(rel0) == need
+        for pf in (1, 2, 5):
+            loc, gets, rel, threads = run(pairs, pf)
+            assert np.array_equal(loc, ref)
+            assert sorted(gets) == need and sorted(rel) == need
+            if pairs:
+                assert threads and threading.current_thread().name not in threads  # prepared off-thread

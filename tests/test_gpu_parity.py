@@ -278,6 +278,28 @@ def test_knn_external_queries_and_small_clouds(ctx):
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
 
 
+def test_knn_sparse_outliers_and_density_jumps(ctx):
+    """The block-growing restart of the k-NN search: isolated outliers metres away from a dense
+    surface (what StatisticalOutlierRemoval exists for), a 100x density jump, and a line of points
+    (degenerate extent in two axes)."""
+    rng = np.random.default_rng(11)
+    dense = np.c_[rng.uniform(0, 0.2, (30000, 2)), rng.normal(0, 1e-4, 30000)]
+    sparse = np.c_[rng.uniform(0.2, 2.2, (3000, 2)), rng.normal(0, 1e-3, 3000)]
+    outliers = rng.uniform(-5, 5, (60, 3))
+    cloud = np.concatenate([dense, sparse, outliers]).astype(np.float32)
+    for k in (5, 51):
+        oi, od = orc.KdTree(cloud).knn(cloud, k)
+        gi, gd = api.knn(cloud, k, ctx=ctx)
+        assert np.array_equal(gd, od) and np.array_equal(gi, oi)
+    kept, md, st = api.sor(cloud, 50, 1.0, ctx=ctx)
+    okept, omd, ost = orc.sor(cloud, 50, 1.0)
+    assert np.array_equal(kept, okept) and np.array_equal(md, omd)
+    line = np.c_[np.linspace(0, 1, 5000), np.zeros(5000), np.zeros(5000)].astype(np.float32)
+    oi, od = orc.KdTree(line).knn(line, 12)
+    gi, gd = api.knn(line, 12, ctx=ctx)
+    assert np.array_equal(gd, od) and np.array_equal(gi, oi)
+
+
 # ----------------------------------------------------------------------------- normals
 
 def test_normals_match_oracle(ctx, pair):
