@@ -1,4 +1,5 @@
 // capi.cu — the C ABI of include/lc3d.h over the CUDA kernels.  No CPU fallback.
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -61,6 +62,63 @@ const unsigned char* stage_raw(lc3d_ctx* ctx, DevBuf& buf, const void* host, int
   return buf.as<unsigned char>();
 }
 
+// Pageable (unregistered) host memory?  cudaMemcpyAsync from it is staged by the driver at a
+// fraction of the PCIe rate and blocks the calling thread.
+bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr int64_t kPackMinPoints = 32768;   // below this the plain copy wins
+constexpr int64_t kPackChunkPoints = 32768; // 384 KiB of packed floats per DMA
+
+// n records of 12 bytes at `stride` in PAGEABLE host memory -> device, packed (stride 12): host
+// threads gather chunk after chunk into pinned staging memory and each finished chunk goes out
+// with its own cudaMemcpyAsync on `cs`, so the DMA of one chunk overlaps the packing of the next
+// and a 48-byte PCL point costs 12 bytes of PCIe per field instead of 48.  Returns the device
+// pointer; the caller's buffer has been consumed when this returns.
+const unsigned char* stage_packed(lc3d_ctx* ctx, int slot, DevBuf& buf, const void* host, int64_t stride, int64_t n,
+                                  cudaStream_t cs) {
+  if (n == 0) return nullptr;
+  cudaStream_t st = cs ? cs : ctx->stream;
+  buf.ensure((size_t)n * 12 + 64);
+  if (!ctx->host_pool) {
+    int t = 3;
+    if (const char* e = std::getenv("LC3D_PACK_THREADS")) t = std::max(0, std::atoi(e) - 1);
+    ctx->host_pool = new HostPool(std::min(t, std::max(0, (int)std::thread::hardware_concurrency() - 1)));
+  }
+  if (!ctx->stage_done[slot]) LC3D_CUDA(cudaEventCreateWithFlags(&ctx->stage_done[slot], cudaEventDisableTiming));
+  else LC3D_CUDA(cudaEventSynchronize(ctx->stage_done[slot]));  // the slot's previous DMA has left it
+  ctx->stage[slot].ensure((size_t)n * 12);
+  unsigned char* pin = ctx->stage[slot].as<unsigned char>();
+  unsigned char* dev = buf.as<unsigned char>();
+  const unsigned char* src = static_cast<const unsigned char*>(host);
+  const int njobs = (int)((n + kPackChunkPoints - 1) / kPackChunkPoints);
+  const int device = ctx->device;
+  std::atomic<int> failed{0};
+  ctx->host_pool->run(njobs, [&](int j) {
+    const int64_t a = (int64_t)j * kPackChunkPoints, b = std::min(n, a + kPackChunkPoints);
+    if (stride == 12) {
+      std::memcpy(pin + a * 12, src + a * 12, (size_t)(b - a) * 12);
+    } else {
+      for (int64_t i = a; i < b; ++i) std::memcpy(pin + i * 12, src + i * stride, 12);
+    }
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaMemcpyAsync(dev + a * 12, pin + a * 12, (size_t)(b - a) * 12, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      failed.store(1);
+  });
+  if (failed.load()) {
+    cudaGetLastError();
+    throw CudaError{"staged upload failed"};
+  }
+  LC3D_CUDA(cudaEventRecord(ctx->stage_done[slot], st));
+  return dev;
+}
+
 // An upload in flight: the raw strided bytes are copied on a (possibly separate) copy stream;
 // the unpack into SoA float4 happens later on the compute stream.
 struct PendingUpload {
@@ -72,6 +130,10 @@ struct PendingUpload {
   // normals staged separately (upload_begin_normals) so that other arrays can go first
   bool normals_deferred = false;
   cudaEvent_t ready_nrm = nullptr;
+  // strides of the STAGED records (12 when the host packed them, else the caller's)
+  int64_t stride_xyz = 0, stride_nrm = 0;
+  int slot = 0;        // staging slots slot (xyz) and slot + 1 (normals)
+  bool packed = false; // pageable input packed by the host pool
 };
 
 PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, bool want_normals, DevBuf& raw_a,
@@ -93,6 +155,30 @@ PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, b
     if (h->normal_stride < 12) throw CudaError{"normal_stride < 12"};
     if (h->normal_stride % 4 != 0) throw CudaError{"cloud.normal_stride must be a multiple of 4 bytes"};
     d->normal.ensure((size_t)n * 16);
+  }
+  pu.slot = (&raw_a == &ctx->scratch[kScrRawA]) ? 0 : 2;
+  pu.stride_xyz = h->xyz_stride;
+  pu.stride_nrm = h->normal_stride;
+  // pageable host memory (std::vector, numpy): the host pool packs every field into pinned staging
+  // memory — 12 bytes per point and field over PCIe whatever the caller's record size
+  pu.packed = n >= kPackMinPoints && host_is_pageable(h->xyz) && !std::getenv("LC3D_NO_PACK");
+  if (pu.packed) {
+    pu.raw_xyz = stage_packed(ctx, pu.slot, raw_a, h->xyz, h->xyz_stride, n, cs);
+    pu.stride_xyz = 12;
+    if (want_normals && h->normal) {
+      if (defer_normals) {
+        pu.normals_deferred = true;
+      } else {
+        pu.raw_nrm = stage_packed(ctx, pu.slot + 1, raw_b, h->normal, h->normal_stride, n, cs);
+        pu.stride_nrm = 12;
+      }
+      d->has_normal = true;
+    }
+    if (ready) {
+      LC3D_CUDA(cudaEventRecord(ready, cs ? cs : ctx->stream));
+      pu.ready = ready;
+    }
+    return pu;
   }
   // same AoS block as xyz (PCL 48-byte points)?  then one staged copy carries both
   const ptrdiff_t off = h->normal ? (const char*)h->normal - (const char*)h->xyz : -1;
@@ -119,7 +205,12 @@ PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, b
 // caller queued in between) with their own completion event.
 void upload_begin_normals(lc3d_ctx* ctx, PendingUpload& pu, DevBuf& raw_b, cudaStream_t cs, cudaEvent_t ready) {
   if (!pu.normals_deferred || pu.h->n == 0) return;
-  pu.raw_nrm = stage_raw(ctx, raw_b, pu.h->normal, pu.h->normal_stride, pu.h->n, 12, cs);
+  if (pu.packed) {
+    pu.raw_nrm = stage_packed(ctx, pu.slot + 1, raw_b, pu.h->normal, pu.h->normal_stride, pu.h->n, cs);
+    pu.stride_nrm = 12;
+  } else {
+    pu.raw_nrm = stage_raw(ctx, raw_b, pu.h->normal, pu.h->normal_stride, pu.h->n, 12, cs);
+  }
   LC3D_CUDA(cudaEventRecord(ready, cs ? cs : ctx->stream));
   pu.ready_nrm = ready;
 }
@@ -127,7 +218,7 @@ void upload_begin_normals(lc3d_ctx* ctx, PendingUpload& pu, DevBuf& raw_b, cudaS
 void upload_finish_normals(lc3d_ctx* ctx, const PendingUpload& pu) {
   if (!pu.normals_deferred || pu.h->n == 0) return;
   LC3D_CUDA(cudaStreamWaitEvent(ctx->stream, pu.ready_nrm, 0));
-  LC3D_LAUNCH(ctx, unpack_strided, div_up(pu.h->n, 256), 256, 0, pu.raw_nrm, pu.h->normal_stride, (int)pu.h->n,
+  LC3D_LAUNCH(ctx, unpack_strided, div_up(pu.h->n, 256), 256, 0, pu.raw_nrm, pu.stride_nrm, (int)pu.h->n,
               0.0f, (const unsigned char*)nullptr, (int64_t)0, pu.d->normal.as<float4>());
 }
 
@@ -135,10 +226,10 @@ void upload_finish(lc3d_ctx* ctx, const PendingUpload& pu) {
   const int64_t n = pu.h->n;
   if (n == 0) return;
   if (pu.ready) LC3D_CUDA(cudaStreamWaitEvent(ctx->stream, pu.ready, 0));
-  LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_xyz, pu.h->xyz_stride, (int)n, 1.0f,
+  LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_xyz, pu.stride_xyz, (int)n, 1.0f,
               (const unsigned char*)nullptr, (int64_t)0, pu.d->xyz.as<float4>());
   if (pu.raw_nrm && !pu.normals_deferred) {
-    LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_nrm, pu.h->normal_stride, (int)n, 0.0f,
+    LC3D_LAUNCH(ctx, unpack_strided, div_up(n, 256), 256, 0, pu.raw_nrm, pu.stride_nrm, (int)n, 0.0f,
                 (const unsigned char*)nullptr, (int64_t)0, pu.d->normal.as<float4>());
     pu.d->has_normal = true;
   }
@@ -657,6 +748,10 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
+  for (auto& b : ctx->stage) b.release();
+  for (auto& e : ctx->stage_done)
+    if (e) cudaEventDestroy(e);
+  delete ctx->host_pool;
   ctx->tmp_a.release();
   ctx->tmp_b.release();
   ctx->pool.release_all();

@@ -5,8 +5,11 @@
 
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lc3d.h"
@@ -73,6 +76,72 @@ struct PinnedBuf {
   T* as() const {
     return reinterpret_cast<T*>(p);
   }
+};
+
+// Fork-join pool of host threads (packing of pageable host clouds into pinned staging memory).
+class HostPool {
+ public:
+  explicit HostPool(int nthreads) {
+    for (int t = 0; t < nthreads; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // runs job(0..njobs-1) on the workers and the calling thread; returns when all are done
+  void run(int njobs, const std::function<void(int)>& job) {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      job_ = &job;
+      next_ = 0;
+      njobs_ = njobs;
+      pending_ = njobs;
+    }
+    cv_.notify_all();
+    for (;;) {  // the caller works too
+      int j;
+      {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (next_ >= njobs_) break;
+        j = next_++;
+      }
+      job(j);
+      std::lock_guard<std::mutex> lock(mu_);
+      --pending_;
+    }
+    std::unique_lock<std::mutex> lock(mu_);
+    done_.wait(lock, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop() {
+    for (;;) {
+      int j;
+      const std::function<void(int)>* job;
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [this] { return stop_ || (job_ && next_ < njobs_); });
+        if (stop_) return;
+        j = next_++;
+        job = job_;
+      }
+      (*job)(j);
+      std::lock_guard<std::mutex> lock(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int next_ = 0, njobs_ = 0, pending_ = 0;
+  bool stop_ = false;
 };
 
 struct Timer {
@@ -231,6 +300,11 @@ struct lc3d_ctx {
   lc3d::Grid* grid = nullptr;  // spatial index reused across calls
   lc3d_dcloud tmp_a, tmp_b;    // staging clouds of the host-buffer entry points
   lc3d::BufPool pool;          // parked buffers of freed resident clouds
+  // pageable host clouds: packed by host threads into pinned staging memory, chunk by chunk, each
+  // chunk's DMA overlapping the packing of the next (slots: target xyz / normals, source xyz / normals)
+  lc3d::PinnedBuf stage[4];
+  cudaEvent_t stage_done[4] = {nullptr, nullptr, nullptr, nullptr};  // last DMA out of the slot
+  lc3d::HostPool* host_pool = nullptr;
   // source-sharded single-pair mode (lc3d_shard_*): exchange buffer + the peers' mappings
   struct Shard {
     int rank = -1, world = 0;

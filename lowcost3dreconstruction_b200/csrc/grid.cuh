@@ -359,8 +359,16 @@ enum { kScrBBox = 0, kScrProbe, kScrKeys, kScrVals, kScrKeysAlt, kScrValsAlt, kS
 //   grid_plan  bbox + density probe + ONE host round trip -> origin, cell edge, dims (everything
 //              a query needs to compute cell coordinates, e.g. the Morton order of the source);
 //   grid_fill  keys, sort, scan, gather (stream-ordered, no host sync).
+// What a caller may already know about the cloud (lc3d_prepare_view after VoxelGrid: every point is
+// finite, lies inside the input's bounding box and the spacing is about the leaf size): with a
+// hint grid_plan runs no kernel and makes no host round trip.
+struct GridHint {
+  float lo[3], hi[3];  // a box that contains every point (not necessarily tight)
+  int64_t nfinite;     // all n points must be finite
+  double spacing;      // estimated point spacing
+};
 inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, double cell_factor,
-                      double min_cell = 0.0, int xsub = 1) {
+                      double min_cell = 0.0, int xsub = 1, const GridHint* hint = nullptr) {
   const int n = (int)n64;
   cudaStream_t st = ctx->stream;
   G.v = GridDev{};
@@ -379,30 +387,39 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
     G.v.pts = G.pts.as<float4>();
     return;
   }
-  // 1. bounding box of the finite points
-  ctx->scratch[kScrBBox].ensure(sizeof(BBoxOut) + 16);
-  BBoxOut* d_bb = ctx->scratch[kScrBBox].as<BBoxOut>();
-  LC3D_LAUNCH(ctx, bbox_init, 1, 32, 0, d_bb);
-  int nb = std::min(div_up(n, 256), ctx->num_sms * 2);
-  LC3D_LAUNCH(ctx, bbox_reduce, nb, 256, 0, xyz, n, d_bb);
-  // 2. density probe (64^3 occupancy over the bbox, bbox read on the device), then ONE round trip
-  const int nwords = kProbe * kProbe * kProbe / 32;
-  ctx->scratch[kScrProbe].ensure(nwords * 4 + 16);
-  uint32_t* bits = ctx->scratch[kScrProbe].as<uint32_t>();
-  LC3D_CUDA(cudaMemsetAsync(bits, 0, nwords * 4 + 16, st));
-  LC3D_LAUNCH(ctx, probe_mark, div_up(n, 256), 256, 0, xyz, n, d_bb, bits);
-  LC3D_LAUNCH(ctx, probe_count, 32, 256, 0, bits, nwords, &d_bb->pad);
-  BBoxOut bb;
-  LC3D_CUDA(cudaMemcpyAsync(&bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, st));
-  LC3D_CUDA(cudaStreamSynchronize(st));
-  const int nfinite = (int)bb.count;
+  BBoxOut bb{};
+  int nfinite = 0;
   double ext[3];
-  if (nfinite == 0) {
-    for (int d = 0; d < 3; ++d) G.lo[d] = G.hi[d] = 0.0f;
-  } else {
+  if (hint) {
+    nfinite = (int)hint->nfinite;
     for (int d = 0; d < 3; ++d) {
-      G.lo[d] = ord2f(bb.lo[d]);
-      G.hi[d] = ord2f(bb.hi[d]);
+      G.lo[d] = hint->lo[d];
+      G.hi[d] = hint->hi[d];
+    }
+  } else {
+    // 1. bounding box of the finite points
+    ctx->scratch[kScrBBox].ensure(sizeof(BBoxOut) + 16);
+    BBoxOut* d_bb = ctx->scratch[kScrBBox].as<BBoxOut>();
+    LC3D_LAUNCH(ctx, bbox_init, 1, 32, 0, d_bb);
+    int nb = std::min(div_up(n, 256), ctx->num_sms * 2);
+    LC3D_LAUNCH(ctx, bbox_reduce, nb, 256, 0, xyz, n, d_bb);
+    // 2. density probe (64^3 occupancy over the bbox, bbox read on the device), then ONE round trip
+    const int nwords = kProbe * kProbe * kProbe / 32;
+    ctx->scratch[kScrProbe].ensure(nwords * 4 + 16);
+    uint32_t* bits = ctx->scratch[kScrProbe].as<uint32_t>();
+    LC3D_CUDA(cudaMemsetAsync(bits, 0, nwords * 4 + 16, st));
+    LC3D_LAUNCH(ctx, probe_mark, div_up(n, 256), 256, 0, xyz, n, d_bb, bits);
+    LC3D_LAUNCH(ctx, probe_count, 32, 256, 0, bits, nwords, &d_bb->pad);
+    LC3D_CUDA(cudaMemcpyAsync(&bb, d_bb, sizeof bb, cudaMemcpyDeviceToHost, st));
+    LC3D_CUDA(cudaStreamSynchronize(st));
+    nfinite = (int)bb.count;
+    if (nfinite == 0) {
+      for (int d = 0; d < 3; ++d) G.lo[d] = G.hi[d] = 0.0f;
+    } else {
+      for (int d = 0; d < 3; ++d) {
+        G.lo[d] = ord2f(bb.lo[d]);
+        G.hi[d] = ord2f(bb.hi[d]);
+      }
     }
   }
   double maxext = 0;
@@ -414,6 +431,9 @@ inline void grid_plan(lc3d_ctx* ctx, Grid& G, const float4* xyz, int64_t n64, do
   double cell, spacing_est = 0.0;
   if (nfinite <= 1 || maxext <= 0) {
     cell = maxext > 0 ? maxext : 1.0;
+  } else if (hint && hint->spacing > 0) {
+    spacing_est = hint->spacing;
+    cell = cell_factor * spacing_est;
   } else {
     double pe[3];
     for (int d = 0; d < 3; ++d) pe[d] = std::max(ext[d], maxext * 1e-6) / kProbe;
@@ -583,8 +603,8 @@ inline void grid_attach_normals(lc3d_ctx* ctx, Grid& G, const float4* nrm, int64
 }
 
 inline void grid_build(lc3d_ctx* ctx, Grid& G, const float4* xyz, const float4* nrm, int64_t n64,
-                       double cell_factor, double min_cell = 0.0, int xsub = 1) {
-  grid_plan(ctx, G, xyz, n64, cell_factor, min_cell, xsub);
+                       double cell_factor, double min_cell = 0.0, int xsub = 1, const GridHint* hint = nullptr) {
+  grid_plan(ctx, G, xyz, n64, cell_factor, min_cell, xsub, hint);
   grid_fill(ctx, G, xyz, nrm, n64);
 }
 
