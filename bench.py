@@ -216,7 +216,9 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
 
     # LANES host threads share the GPU, each with two contexts (own streams, own scratch): one aligns
     # the pairs of its sub-block, the other runs the per-view passes one view ahead (chain.align_pairs)
-    n_lanes = max(1, min(CHAIN_LANES, len(pairs)))
+    # (a second pipeline costs one more view preparation - the sub-blocks' border view - which only
+    # pays off when the rank has enough pairs to amortise it)
+    n_lanes = CHAIN_LANES if len(pairs) >= 4 * CHAIN_LANES else 1
     icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_lanes - 1)]
     prep_ctx = [api.Context(ctx.device) for _ in range(n_lanes)]
     pinned = {v: api.host_register(a) for v, a in raw.items()}  # the PLY loader's buffers, pinned once

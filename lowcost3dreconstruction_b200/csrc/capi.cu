@@ -313,7 +313,17 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   // plan (bbox, cell size: one host round trip), then the target fill (keys, sort, scan, gather)
   // runs on the auxiliary stream while this stream orders the source along the Morton curve of
   // the planned cells — two independent chains of short launch-bound kernels
-  grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env());
+  GridHint hint{};
+  if (tgt->has_hint && !std::getenv("LC3D_NO_GRID_HINT")) {
+    for (int d = 0; d < 3; ++d) {
+      hint.lo[d] = tgt->hint_lo[d];
+      hint.hi[d] = tgt->hint_hi[d];
+    }
+    hint.nfinite = tgt->n;
+    hint.spacing = tgt->hint_spacing;
+  }
+  grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env(),
+            hint.nfinite > 0 ? &hint : nullptr);
   // host-buffer point-to-plane: the target normals are still crossing PCIe — build the index and
   // run the search of iteration 0 without them, gather them into index order afterwards and let
   // icp_estimate_kernel compute iteration 0's sums (LC3D_DEFER_NORMALS=0 switches it off)

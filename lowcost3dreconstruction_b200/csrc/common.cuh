@@ -265,11 +265,17 @@ struct lc3d_dcloud {
   lc3d::DevBuf xyz;     // float4 (x,y,z,1) in input order
   lc3d::DevBuf normal;  // float4 (nx,ny,nz,curvature) in input order, or empty
   bool has_normal = false;
+  // what lc3d_prepare_view knows about the cloud it produced (all points finite, inside this box,
+  // about `spacing` apart): lets the ICP index be planned without kernels or a host round trip
+  bool has_hint = false;
+  float hint_lo[3] = {0, 0, 0}, hint_hi[3] = {0, 0, 0};
+  double hint_spacing = 0.0;
   void release() {
     xyz.release();
     normal.release();
     n = 0;
     has_normal = false;
+    has_hint = false;
   }
   // buffers go back to the context's pool instead of cudaFree
   void park(lc3d::BufPool& pool) {
@@ -277,6 +283,7 @@ struct lc3d_dcloud {
     pool.park(normal);
     n = 0;
     has_normal = false;
+    has_hint = false;
   }
 };
 

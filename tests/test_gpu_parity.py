@@ -236,6 +236,26 @@ def test_icp_pcl_aos_layout_and_resident(ctx, pair_normals):
     dt.free()
 
 
+def test_icp_pinned_and_pageable_host_buffers_agree(ctx, pair_normals):
+    """Host-buffer ICP takes two upload paths: page-locked memory goes out with plain async copies
+    of the caller's records, pageable memory is packed by the host thread pool into pinned staging
+    chunks.  Same bits either way (and the same as with the deferred-normals iteration 0 off)."""
+    src, tgt = pair_normals
+    ref = api.icp_align(src, tgt, 0.02, 30, mode=1, want_registered=True, ctx=ctx)  # pageable numpy arrays
+    arrs = [api.host_register(np.array(a, dtype=np.float32, order="C", copy=True))
+            for a in (src.xyz, src.normal, tgt.xyz, tgt.normal)]
+    try:
+        g = api.icp_align(HostCloud(arrs[0], normal=arrs[1]), HostCloud(arrs[2], normal=arrs[3]), 0.02, 30, mode=1,
+                          want_registered=True, ctx=ctx)
+    finally:
+        for a in arrs:
+            api.host_unregister(a)
+    assert np.array_equal(g["transformation"], ref["transformation"]) and g["fitness"] == ref["fitness"]
+    assert g["iterations"] == ref["iterations"]
+    assert np.array_equal(g["registered_xyz"], ref["registered_xyz"])
+    assert np.array_equal(g["registered_normal"], ref["registered_normal"])
+
+
 def test_icp_equivariance_property(ctx, pair):
     """Size-independent property: moving both clouds by a rigid motion M
     conjugates the solution, T' = M T M^-1, up to float rounding."""
