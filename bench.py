@@ -44,7 +44,7 @@ CHAIN_VIEWS = 36
 CHAIN_STEP = 360.0 / CHAIN_VIEWS
 CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL = 0.002, 50, 1.0
 CHAIN_PREFETCH = int(os.environ.get("LC3D_CHAIN_PREFETCH", "1"))  # views prepared ahead on a worker thread (0 = serial)
-CHAIN_LANES = int(os.environ.get("LC3D_CHAIN_LANES", "2"))  # host threads (pair sub-blocks) per GPU
+CHAIN_LANES = int(os.environ.get("LC3D_CHAIN_LANES", "3"))  # host threads (pair sub-blocks) per GPU
 
 
 # ------------------------------------------------------------------------------------ inputs
@@ -218,7 +218,7 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     # the pairs of its sub-block, the other runs the per-view passes one view ahead (chain.align_pairs)
     # (a second pipeline costs one more view preparation - the sub-blocks' border view - which only
     # pays off when the rank has enough pairs to amortise it)
-    n_lanes = CHAIN_LANES if len(pairs) >= 4 * CHAIN_LANES else 1
+    n_lanes = max(1, min(CHAIN_LANES, len(pairs) // 4))
     icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_lanes - 1)]
     prep_ctx = [api.Context(ctx.device) for _ in range(n_lanes)]
     pinned = {v: api.host_register(a) for v, a in raw.items()}  # the PLY loader's buffers, pinned once
@@ -241,15 +241,23 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
         chain.align_pairs_lanes(pairs, [lane(i) for i in range(n_lanes)], local, prefetch=CHAIN_PREFETCH)
         return chain.exchange_records(local, dev), npts  # one gather per chain (20 doubles per pair)
 
+    # the lanes are Python threads whose work is inside GIL-releasing C calls; a short switch interval
+    # keeps the hand-offs between them from waiting on the interpreter's default 5 ms tick
+    switch0 = sys.getswitchinterval()
+    sys.setswitchinterval(5e-5)
     one_chain()  # warm-up: allocations, NCCL communicator
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    rep_s = []
     for _ in range(reps):
+        r0 = time.perf_counter()
         rec, npts = one_chain()
+        rep_s.append(time.perf_counter() - r0)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    sys.setswitchinterval(switch0)
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -275,6 +283,7 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
             "points_per_view_after_voxel_sor": int(np.mean(npts)) if npts else 0,
             "pose_35_translation_m": [float(x) for x in poses[-1][:3, 3]],
             "prefetch_views": CHAIN_PREFETCH, "lanes_per_gpu": n_lanes,
+            "rank0_seconds_per_repetition": [round(x, 5) for x in rep_s],
             "timed": "per view VoxelGrid 2 mm + SOR k=50 + normals k=30 on the device (lc3d_prepare_view, page-locked host "
                      "xyz in, on a second context one view ahead of the pair being aligned), per pair point-to-plane "
                      "ICP on the resident views, one record gather per chain; wall clock bracketed by barrier + cuda "
@@ -291,7 +300,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chain", action="store_true")
-    ap.add_argument("--chain-reps", type=int, default=3)
+    ap.add_argument("--chain-reps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

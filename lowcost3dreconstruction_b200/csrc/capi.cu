@@ -73,7 +73,7 @@ bool host_is_pageable(const void* p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
-constexpr int64_t kPackMinPoints = 32768;   // below this the plain copy wins
+constexpr int64_t kPackMinPoints = 131072;  // below this the plain copy wins (pool wake-up, per-chunk calls)
 constexpr int64_t kPackChunkPoints = 32768; // 384 KiB of packed floats per DMA
 
 // n records of 12 bytes at `stride` in PAGEABLE host memory -> device, packed (stride 12): host
@@ -161,7 +161,12 @@ PendingUpload upload_begin(lc3d_ctx* ctx, const lc3d_cloud* h, lc3d_dcloud* d, b
   pu.stride_nrm = h->normal_stride;
   // pageable host memory (std::vector, numpy): the host pool packs every field into pinned staging
   // memory — 12 bytes per point and field over PCIe whatever the caller's record size
-  pu.packed = n >= kPackMinPoints && host_is_pageable(h->xyz) && !std::getenv("LC3D_NO_PACK");
+  // (packed 12-byte arrays gain nothing: the driver's own pageable staging runs at the same host
+  // memcpy rate; records wider than the fields that are used — PCL's 48-byte points — halve their PCIe
+  // bytes)
+  int64_t pack_min = kPackMinPoints;
+  if (const char* e = std::getenv("LC3D_PACK_MIN")) pack_min = std::max(1, std::atoi(e));
+  pu.packed = n >= pack_min && h->xyz_stride > 16 && host_is_pageable(h->xyz) && !std::getenv("LC3D_NO_PACK");
   if (pu.packed) {
     pu.raw_xyz = stage_packed(ctx, pu.slot, raw_a, h->xyz, h->xyz_stride, n, cs);
     pu.stride_xyz = 12;
@@ -324,12 +329,14 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   }
   grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env(),
             hint.nfinite > 0 ? &hint : nullptr);
-  // host-buffer point-to-plane: the target normals are still crossing PCIe — build the index and
-  // run the search of iteration 0 without them, gather them into index order afterwards and let
-  // icp_estimate_kernel compute iteration 0's sums (LC3D_DEFER_NORMALS=0 switches it off)
+  // host-buffer point-to-plane, LC3D_DEFER_NORMALS=1 (for hosts with a slow PCIe link): while the
+  // target normals are still in flight, build the index and run the search of iteration 0 without
+  // them, gather them into index order afterwards and let icp_estimate_kernel compute iteration 0's
+  // sums.  Off by default: at the 43 GB/s these boxes move, the normals land 40 us after the index
+  // is built and the extra gather + estimate launches cost 30 us (profiles/r02_summary.md).
   const bool defer_normals = hooks.before_target_normals && p->mode == LC3D_ICP_POINT_TO_PLANE && tgt->has_normal &&
                              tgt->n > 0 && n > 0 && !sharded && !std::getenv("LC3D_STATS") &&
-                             !(std::getenv("LC3D_DEFER_NORMALS") && std::atoi(std::getenv("LC3D_DEFER_NORMALS")) == 0);
+                             std::getenv("LC3D_DEFER_NORMALS") && std::atoi(std::getenv("LC3D_DEFER_NORMALS")) != 0;
   const bool two_streams = ctx->aux_stream != nullptr && !std::getenv("LC3D_NO_AUX");
   {
     struct StreamSwap {

@@ -258,40 +258,25 @@ __device__ __forceinline__ bool nn_ball_warp(const GridDev& g, float qx, float q
   const float inv_side = 1.0f / (float)side;
   Best lb = b;
   float bd = b.d2;
-  // kBallRows rows per lane and step: their cell_start loads are independent, so one step pays the
-  // dependent cell_start -> point -> compare latency once for 32 * kBallRows rows (a far query is a
-  // chain of such steps and nothing else runs in the warp: the walk is latency-bound)
-#ifndef LC3D_BALL_ROWS
-#define LC3D_BALL_ROWS 3
-#endif
-  constexpr int kBallRows = LC3D_BALL_ROWS;
-  for (int t0 = 0; t0 < total; t0 += 32 * kBallRows) {
-    uint32_t rs[kBallRows], re[kBallRows];
-#pragma unroll
-    for (int u = 0; u < kBallRows; ++u) {
-      rs[u] = re[u] = 0;
-      const int t = t0 + u * 32 + lane;
-      if (t < total) {
-        const int rz = (int)(((float)t + 0.5f) * inv_side);  // exact: t < 33^2
-        const int dy = t - rz * side - W, dz = rz - W;
-        const int yy = qc.iy + dy, zz = qc.iz + dz;
-        if ((unsigned)yy < (unsigned)g.dy && (unsigned)zz < (unsigned)g.dz) {
-          const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
-          const float rem = bd * inv_c2 - (gy * gy + gz * gz);
-          if (rem >= 0.0f) {
-            const float wx = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
-            const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
-            if (xa <= xb) {
-              const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
-              rs[u] = __ldg(row + xa);
-              re[u] = __ldg(row + xb + 1);
-            }
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    if (t < total) {
+      const int rz = (int)(((float)t + 0.5f) * inv_side);  // exact: t < 33^2
+      const int dy = t - rz * side - W, dz = rz - W;
+      const int yy = qc.iy + dy, zz = qc.iz + dz;
+      if ((unsigned)yy < (unsigned)g.dy && (unsigned)zz < (unsigned)g.dz) {
+        const float gy = slab_gap(qc.fy, yy, yy), gz = slab_gap(qc.fz, zz, zz);
+        const float rem = bd * inv_c2 - (gy * gy + gz * gz);
+        if (rem >= 0.0f) {
+          const float wx = (sqrtf(rem) + 2.0f * kCellSlack) * (float)g.xs;  // x-subcells
+          const int xa = max((int)floorf(qc.fx - wx), 0), xb = min((int)floorf(qc.fx + wx), g.dx - 1);
+          if (xa <= xb) {
+            const uint32_t* row = g.cell_start + (size_t)(zz * g.dy + yy) * g.dx;
+            scan_run(g.pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, lb);
           }
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kBallRows; ++u) scan_run(g.pts, rs[u], re[u], qx, qy, qz, lb);
     bd = fminf(bd, warp_min_f(lb.d2));
   }
   // lexicographic (d2, original index) min over the lanes

@@ -236,6 +236,35 @@ def test_icp_pcl_aos_layout_and_resident(ctx, pair_normals):
     dt.free()
 
 
+def test_icp_packed_staging_of_pageable_aos_records(ctx, pair_normals, monkeypatch):
+    """Pageable 48-byte pcl::PointXYZRGBNormal records above LC3D_PACK_MIN points are packed by the
+    host thread pool into pinned staging chunks (12 bytes per point and field): same bits as the
+    plain copy of the caller's records."""
+    src, tgt = pair_normals
+
+    def aos(hc):
+        a = np.zeros((hc.n, 12), dtype=np.float32)
+        a[:, 0:3] = hc.xyz
+        a[:, 3] = 1.0
+        a[:, 4:7] = hc.normal
+        a[:, 9] = hc.curvature
+        return HostCloud.from_pcl_aos(a)
+
+    S, T = aos(src), aos(tgt)
+    monkeypatch.setenv("LC3D_NO_PACK", "1")
+    ref = api.icp_align(S, T, 0.02, 30, mode=1, want_registered=True, ctx=ctx)
+    monkeypatch.delenv("LC3D_NO_PACK")
+    monkeypatch.setenv("LC3D_PACK_MIN", "1000")
+    for threads in ("1", "4"):
+        monkeypatch.setenv("LC3D_PACK_THREADS", threads)  # (read when the context creates its pool)
+        c2 = api.Context(0)
+        g = api.icp_align(S, T, 0.02, 30, mode=1, want_registered=True, ctx=c2)
+        c2.close()
+        assert np.array_equal(g["transformation"], ref["transformation"]) and g["fitness"] == ref["fitness"]
+        assert np.array_equal(g["registered_xyz"], ref["registered_xyz"])
+        assert np.array_equal(g["registered_normal"], ref["registered_normal"])
+
+
 def test_icp_pinned_and_pageable_host_buffers_agree(ctx, pair_normals):
     """Host-buffer ICP takes two upload paths: page-locked memory goes out with plain async copies
     of the caller's records, pageable memory is packed by the host thread pool into pinned staging
