@@ -245,7 +245,8 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     # keeps the hand-offs between them from waiting on the interpreter's default 5 ms tick
     switch0 = sys.getswitchinterval()
     sys.setswitchinterval(5e-5)
-    one_chain()  # warm-up: allocations, NCCL communicator
+    for _ in range(2):
+        one_chain()  # warm-up: allocations in every lane's pools, NCCL communicator
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

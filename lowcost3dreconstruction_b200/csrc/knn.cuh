@@ -281,6 +281,8 @@ struct KnnArgs {
 };
 
 template <int CAP, int CONSUMER>
+// (56 registers, 9 blocks per SM; forcing 12 or 16 blocks or allowing 80 registers changes the SOR /
+// normals stages by less than the run-to-run spread: the warps wait on the shared-memory sort)
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_constant__ GridDev g, const __grid_constant__ KnnArgs a) {
   __shared__ unsigned long long sbuf[kKnnWarps][CAP];
   __shared__ float snb[CONSUMER == kConsumeNormals ? kKnnWarps : 1][CONSUMER == kConsumeNormals ? CAP : 1][3];
