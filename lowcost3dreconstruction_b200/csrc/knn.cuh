@@ -46,6 +46,52 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* buf, int l
   }
 }
 
+// The same network with the keys in registers: element i = r * 32 + lane lives in register r of its
+// lane, so compare-exchange distances below 32 are one __shfl_xor per key and distances of 32 and
+// more pair two registers of the same lane.  Same instruction count as the shared-memory version
+// but half its dependent latency per step (no load -> compare -> store -> __syncwarp round trip), and
+// the R keys of a lane are independent work — the k-NN kernels wait on this sort.
+// buf[0..cnt) in, buf[0..32R) sorted ascending out (padded with kMaxKey).
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort_regs(unsigned long long* buf, int cnt, int lane) {
+  const unsigned full = 0xffffffffu;
+  unsigned long long v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = (r * 32 + lane < cnt) ? buf[r * 32 + lane] : 0xffffffffffffffffull;
+#pragma unroll
+  for (int kk = 2; kk <= 32 * R; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int jr = j >> 5;
+          if ((r & jr) == 0) {
+            const bool asc = ((r * 32) & kk) == 0;  // kk >= 64 here: the lane bits do not matter
+            const unsigned long long a = v[r], b = v[r ^ jr];
+            const bool sw = (a > b) == asc;
+            v[r] = sw ? b : a;
+            v[r ^ jr] = sw ? a : b;
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool asc = ((r * 32 + lane) & kk) == 0;
+          const unsigned long long a = v[r];
+          const unsigned long long b = __shfl_xor_sync(full, a, j);
+          const bool take_min = lower == asc;
+          v[r] = ((a < b) == take_min) ? a : b;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) buf[r * 32 + lane] = v[r];
+  __syncwarp();
+}
+
 template <int CAP>
 struct KnnState {
   unsigned long long* buf;  // CAP keys, per warp, shared memory
@@ -59,13 +105,25 @@ struct KnnState {
 template <int CAP>
 __device__ __forceinline__ void knn_sort_truncate(KnnState<CAP>& s, int lane) {
   const int n = s.cnt <= 32 ? 32 : s.cnt <= 64 ? 64 : s.cnt <= 128 ? 128 : s.cnt <= 256 ? 256 : 512;
-  for (int t = s.cnt + lane; t < n; t += 32) s.buf[t] = kMaxKey;
-  __syncwarp();
-  if (n == 32) warp_bitonic_sort<32>(s.buf, lane);
-  else if (n == 64) warp_bitonic_sort<(CAP >= 64 ? 64 : CAP)>(s.buf, lane);
-  else if (n == 128) warp_bitonic_sort<(CAP >= 128 ? 128 : CAP)>(s.buf, lane);
-  else if (n == 256) warp_bitonic_sort<(CAP >= 256 ? 256 : CAP)>(s.buf, lane);
-  else warp_bitonic_sort<CAP>(s.buf, lane);
+#ifndef LC3D_KNN_SMEM_SORT
+  __syncwarp();  // the appended keys are visible to every lane
+  if (n == 32) {
+    warp_bitonic_sort_regs<1>(s.buf, s.cnt, lane);
+  } else if (n == 64) {
+    warp_bitonic_sort_regs<(CAP >= 64 ? 2 : 1)>(s.buf, s.cnt, lane);
+  } else if (n == 128) {
+    warp_bitonic_sort_regs<(CAP >= 128 ? 4 : 1)>(s.buf, s.cnt, lane);
+  } else
+#endif
+  {
+    for (int t = s.cnt + lane; t < n; t += 32) s.buf[t] = kMaxKey;
+    __syncwarp();
+    if (n == 32) warp_bitonic_sort<32>(s.buf, lane);
+    else if (n == 64) warp_bitonic_sort<(CAP >= 64 ? 64 : CAP)>(s.buf, lane);
+    else if (n == 128) warp_bitonic_sort<(CAP >= 128 ? 128 : CAP)>(s.buf, lane);
+    else if (n == 256) warp_bitonic_sort<(CAP >= 256 ? 256 : CAP)>(s.buf, lane);
+    else warp_bitonic_sort<CAP>(s.buf, lane);
+  }
   if (s.cnt > s.k) s.cnt = s.k;
   s.thresh = s.cnt == s.k ? s.buf[s.k - 1] : kMaxKey;
 }
