@@ -323,6 +323,22 @@ def main():
     from lowcost3dreconstruction_b200 import api
     from lowcost3dreconstruction_b200._capi import HostCloud
 
+    # host threads and pinned buffers next to the GPU: NVML's CPU affinity of the device (the cores of
+    # its NUMA node).  The e2e arm is a host-side wall clock over PCIe copies from pinned memory; a
+    # process that lands on the far socket sees 30 % less of it.
+    affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cores &= set(os.sched_getaffinity(0))
+        if cores:
+            os.sched_setaffinity(0, cores)
+            affinity = len(cores)
+    except Exception:  # noqa: BLE001 - best effort (no NVML, containers without the syscall)
+        pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -425,7 +441,9 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             r = api.icp_align(Sx, Tx, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, registered_out=reg_out, ctx=ctx)
-            e_t += time.perf_counter() - t0
+            dt_ = time.perf_counter() - t0
+            e_t += dt_
+            e2e_step_ms.append(dt_ * 1e3)
             e_iters += r["iterations"]
         return reduce_e2e(e_t, e_iters)
 
@@ -436,12 +454,30 @@ def main():
     if chain_in is not None and os.environ.get("LC3D_BENCH_CHAIN_FIRST"):
         chain_res = run_chain(ctx, rank, world, dev, *chain_in, reps=max(1, args.chain_reps))
         chain_in = None
-    e_reps = max(3, min(args.steps, 10))
+    e_reps = max(3, min(args.steps, 20))
+    e2e_step_ms: list[float] = []
+
+    def pcie_rates():
+        a = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        out = []
+        for src_, dst_ in ((a, d), (d, a)):
+            for _ in range(2):
+                dst_.copy_(src_, non_blocking=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                dst_.copy_(src_, non_blocking=True)
+            torch.cuda.synchronize()
+            out.append(4 * 64 / 1024 / (time.perf_counter() - t0))
+        return out
+    pcie_h2d, pcie_d2h = pcie_rates()
     # (a) headline: packed arrays in pinned host memory (what a caller that owns its buffers does)
     keep = [pinned(x) for x in (src, n_s, tgt, n_t, np.empty_like(src), np.empty_like(src))]
     Sp = HostCloud(keep[0][1], normal=keep[1][1])
     Tp = HostCloud(keep[2][1], normal=keep[3][1])
     e2e_val = time_e2e(Sp, Tp, (keep[4][1], keep[5][1]), e_reps)
+    e2e_median_ms = float(np.median(e2e_step_ms))  # (host wall clock: the median shows the jitter of the mean)
     h2d = int(Sp.n * 24 + Tp.n * 24)
     d2h = int(Sp.n * 24 + 128)
     # (b) what INTEGRATION.md's in-main() binding passes: PCL's own 48-byte PointXYZRGBNormal array in
@@ -533,7 +569,9 @@ def main():
                        "step": "index build + ICP loop + fitness on resident clouds"},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "host_memory": "pinned, packed xyz / normal arrays"},
+                    "host_memory": "pinned, packed xyz / normal arrays",
+                    "pcie_pinned_gbs": {"h2d": round(pcie_h2d, 1), "d2h": round(pcie_d2h, 1)},
+                    "cpu_affinity_cores": affinity, "steps": e_reps, "median_ms_per_step": round(e2e_median_ms, 4)},
             "gpu_launches": int(launches), "clocks": clocks,
             "extra": {"iterations_per_alignment": iters / args.steps, "pairs_per_sec": world * args.steps / (ms_max * 1e-3),
                       "ms_index_per_step": ms_index / args.steps, "ms_loop_per_step": ms_loop / args.steps,
