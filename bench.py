@@ -47,6 +47,9 @@ CHAIN_STEP = 360.0 / CHAIN_VIEWS
 CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL = 0.002, 50, 1.0
 CHAIN_PREFETCH = int(os.environ.get("LC3D_CHAIN_PREFETCH", "1"))  # views prepared ahead on a worker thread (0 = serial)
 CHAIN_LANES = int(os.environ.get("LC3D_CHAIN_LANES", "3"))  # host threads (pair sub-blocks) per GPU
+CHAIN_MODE = os.environ.get("LC3D_CHAIN_MODE", "dag")
+CHAIN_PREP = int(os.environ.get("LC3D_CHAIN_PREP", "4"))    # dag mode: view-preparation threads per GPU
+CHAIN_ALIGN = int(os.environ.get("LC3D_CHAIN_ALIGN", "3"))  # dag mode: pair-alignment threads per GPU
 
 
 # ------------------------------------------------------------------------------------ inputs
@@ -216,48 +219,73 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     import torch.distributed as dist
     from lowcost3dreconstruction_b200 import api, chain
 
-    # LANES host threads share the GPU, each with two contexts (own streams, own scratch): one aligns
-    # the pairs of its sub-block, the other runs the per-view passes one view ahead (chain.align_pairs)
-    # (a second pipeline costs one more view preparation - the sub-blocks' border view - which only
-    # pays off when the rank has enough pairs to amortise it)
-    n_lanes = max(1, min(CHAIN_LANES, len(pairs) // 4))
-    icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_lanes - 1)]
-    prep_ctx = [api.Context(ctx.device) for _ in range(n_lanes)]
+    # The rank's block runs as a task graph on its GPU (chain.align_pairs_dag): CHAIN_PREP host threads
+    # prepare views, CHAIN_ALIGN threads align pairs as soon as both views are ready; every thread has
+    # its own lc3d context (own stream, own scratch).  LC3D_CHAIN_MODE=lanes selects the sub-block
+    # pipelines of chain.align_pairs_lanes instead.
+    dag = CHAIN_MODE == "dag"
+    n_lanes = max(1, min(CHAIN_LANES, len(pairs) // 2))
+    n_prep = max(1, min(CHAIN_PREP, len(pairs) + 1)) if dag else n_lanes
+    n_align = max(1, min(CHAIN_ALIGN, len(pairs))) if dag else n_lanes
+    icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_align - 1)]
+    prep_ctx = [api.Context(ctx.device) for _ in range(n_prep)]
     pinned = {v: api.host_register(a) for v, a in raw.items()}  # the PLY loader's buffers, pinned once
 
     def one_chain():
         """this rank's views prepared on the device, its pairs aligned resident"""
         local, npts = np.zeros((CHAIN_VIEWS - 1, chain.RECORD)), []
 
-        def lane(i):
+        def prep_fn(i):
             def get_view(v):
                 d, cnt = api.prepare_view(pinned[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=prep_ctx[i])
                 npts.append(cnt[2])
                 return d
+            return get_view
 
+        def align_fn(i):
             def align(src, tgt):
                 return api.icp_align(src, tgt, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=icp_ctx[i])
+            return align
 
-            return get_view, align, (lambda d: d.free())
-
-        chain.align_pairs_lanes(pairs, [lane(i) for i in range(n_lanes)], local, prefetch=CHAIN_PREFETCH)
+        if dag:
+            chain.align_pairs_dag(pairs, [prep_fn(i) for i in range(n_prep)], [align_fn(i) for i in range(n_align)],
+                                  local, release=lambda d: d.free())
+        else:
+            chain.align_pairs_lanes(pairs, [(prep_fn(i), align_fn(i), (lambda d: d.free())) for i in range(n_lanes)],
+                                    local, prefetch=CHAIN_PREFETCH)
         return chain.exchange_records(local, dev), npts  # one gather per chain (20 doubles per pair)
 
     # the lanes are Python threads whose work is inside GIL-releasing C calls; a short switch interval
     # keeps the hand-offs between them from waiting on the interpreter's default 5 ms tick
     switch0 = sys.getswitchinterval()
     sys.setswitchinterval(5e-5)
+    # warm-up.  Which context handles which view / pair is decided at run time, and the scratch buffers
+    # of a context grow to the largest cloud / cell table it has seen (a regrowth is a cudaFree: a
+    # device-wide synchronisation, 5-25 ms when seven streams are busy): every context sees every view /
+    # pair of the block once, so that the timed repetitions allocate nothing
+    # (rank0_device_allocations_per_repetition).  Then two whole chains (NCCL communicator, pools).
+    if dag:
+        for c in prep_ctx:
+            held = {v: api.prepare_view(pinned[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=c)[0]
+                    for v in sorted({p for p in pairs} | {p - 1 for p in pairs})}
+            if c is prep_ctx[-1]:
+                for ic in icp_ctx:
+                    for p in pairs:
+                        api.icp_align(held[p], held[p - 1], MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=ic)
+            for d in held.values():
+                d.free()
     for _ in range(2):
-        one_chain()  # warm-up: allocations in every lane's pools, NCCL communicator
+        one_chain()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    rep_s = []
+    rep_s, rep_allocs = [], []
     for _ in range(reps):
-        r0 = time.perf_counter()
+        r0, a0 = time.perf_counter(), ctx._lib.lc3d_debug_alloc_count()
         rec, npts = one_chain()
         rep_s.append(time.perf_counter() - r0)
+        rep_allocs.append(int(ctx._lib.lc3d_debug_alloc_count() - a0))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     sys.setswitchinterval(switch0)
@@ -285,8 +313,11 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
             "median_rot_err_deg_vs_truth": float(np.median(errs)), "max_rot_err_deg_vs_truth": float(np.max(errs)),
             "points_per_view_after_voxel_sor": int(np.mean(npts)) if npts else 0,
             "pose_35_translation_m": [float(x) for x in poses[-1][:3, 3]],
+            "schedule": (f"task graph: {n_prep} view-preparation + {n_align} pair-alignment host threads per GPU" if dag
+                         else f"{n_lanes} sub-block pipelines per GPU, prefetch {CHAIN_PREFETCH}"),
             "prefetch_views": CHAIN_PREFETCH, "lanes_per_gpu": n_lanes,
             "rank0_seconds_per_repetition": [round(x, 5) for x in rep_s],
+            "rank0_device_allocations_per_repetition": rep_allocs,
             "timed": "per view VoxelGrid 2 mm + SOR k=50 + normals k=30 on the device (lc3d_prepare_view, page-locked host "
                      "xyz in, on a second context one view ahead of the pair being aligned), per pair point-to-plane "
                      "ICP on the resident views, one record gather per chain; wall clock bracketed by barrier + cuda "

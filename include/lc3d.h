@@ -64,6 +64,9 @@ const char* lc3d_version(void);
 void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]);
 /* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
 int64_t lc3d_launch_count(const lc3d_ctx* ctx);
+/* Device allocations (cudaMalloc of a scratch / cloud buffer) made so far by this process: a
+ * diagnostic for "the steady state allocates nothing" (cudaFree synchronises the whole device). */
+int64_t lc3d_debug_alloc_count(void);
 
 /* Page-locks / releases a caller-owned host range (cudaHostRegister): copies from / to it are
  * then true asynchronous DMA at full PCIe rate instead of staged pageable copies.  Worth it for

@@ -88,7 +88,7 @@ STATE_NAMES = {0: "NOT_CONVERGED", 1: "ITERATIONS", 2: "TRANSFORM", 3: "ABS_MSE"
 # Every symbol include/lc3d.h declares (tests check the library exports all of them).
 SYMBOLS = [
     "lc3d_create", "lc3d_destroy", "lc3d_last_error", "lc3d_version", "lc3d_launch_count",
-    "lc3d_debug_grid_info",
+    "lc3d_debug_grid_info", "lc3d_debug_alloc_count",
     "lc3d_cloud_upload", "lc3d_cloud_free", "lc3d_dcloud_size",
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
@@ -160,6 +160,8 @@ def _declare(lib):
     lib.lc3d_launch_count.restype = i64
     lib.lc3d_debug_grid_info.argtypes = [vp, C.POINTER(C.c_double)]
     lib.lc3d_debug_grid_info.restype = None
+    lib.lc3d_debug_alloc_count.argtypes = []
+    lib.lc3d_debug_alloc_count.restype = i64
     lib.lc3d_cloud_upload.argtypes = [vp, cp, C.POINTER(vp)]
     lib.lc3d_cloud_upload.restype = C.c_int
     lib.lc3d_cloud_free.argtypes = [vp, vp]

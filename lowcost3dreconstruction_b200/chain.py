@@ -151,6 +151,69 @@ def align_pairs_lanes(pairs: Sequence[int], lanes: Sequence[tuple], local: np.nd
         raise errors[0]
 
 
+def align_pairs_dag(pairs: Sequence[int], prep_fns: Sequence[Callable[[int], object]],
+                    align_fns: Sequence[Callable[[object, object], dict]], local: np.ndarray,
+                    release: Callable[[object], None] | None = None) -> None:
+    """The rank's block as a task graph on ONE GPU: prepare(v) for every needed view (each exactly
+    once) on a pool of len(prep_fns) host threads, align(p) as soon as views p and p-1 are ready on a
+    pool of len(align_fns) threads.  Every callable is bound to its own lc3d context (own stream, own
+    scratch) and is used by one thread at a time.  Unlike the sub-block pipelines of
+    align_pairs_lanes no view is prepared twice, and a block of 4-5 pairs (8 GPUs) still keeps several
+    streams busy instead of one pipeline that never reaches its steady state.  A view is released
+    (release(view), from whichever thread finishes its last pair) once no pair needs it any more."""
+    pairs = list(pairs)
+    if not pairs:
+        return
+    import queue
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    views = sorted({p for p in pairs} | {p - 1 for p in pairs})
+    users = {v: sum(1 for p in pairs if v in (p, p - 1)) for v in views}
+    lock = threading.Lock()
+    prep_q: "queue.SimpleQueue" = queue.SimpleQueue()
+    align_q: "queue.SimpleQueue" = queue.SimpleQueue()
+    for f in prep_fns:
+        prep_q.put(f)
+    for f in align_fns:
+        align_q.put(f)
+
+    def do_prep(v):
+        f = prep_q.get()
+        try:
+            return f(v)
+        finally:
+            prep_q.put(f)
+
+    def do_align(p, fsrc, ftgt):
+        src, tgt = fsrc.result(), ftgt.result()
+        f = align_q.get()
+        try:
+            rec = pack_record(f(src, tgt))
+        finally:
+            align_q.put(f)
+        local[p - 1] = rec
+        if release:
+            for v, obj in ((p, src), (p - 1, tgt)):
+                with lock:
+                    users[v] -= 1
+                    last = users[v] == 0
+                if last:
+                    release(obj)
+
+    with ThreadPoolExecutor(max_workers=len(prep_fns), thread_name_prefix="lc3d-prep") as pp, \
+            ThreadPoolExecutor(max_workers=len(align_fns), thread_name_prefix="lc3d-align") as ap:
+        vf = {v: pp.submit(do_prep, v) for v in views}  # ascending: the pairs become ready in order
+        af = [ap.submit(do_align, p, vf[p], vf[p - 1]) for p in pairs]
+        err = None
+        for f in af:
+            try:
+                f.result()
+            except BaseException as e:  # noqa: BLE001 - first error re-raised after the pools drain
+                err = err or e
+        if err:
+            raise err
+
+
 def register_chain(n_views: int, get_view: Callable[[int], object], align: Callable[[object, object], dict],
                    rank: int = 0, world: int = 1, device=None, prefetch: int = 0,
                    release: Callable[[object], None] | None = None) -> dict:

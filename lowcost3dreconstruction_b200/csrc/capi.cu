@@ -808,6 +808,8 @@ void lc3d_debug_grid_info(const lc3d_ctx* ctx, double out[8]) {
   out[5] = g.n;
 }
 
+int64_t lc3d_debug_alloc_count(void) { return (int64_t)lc3d::devbuf_alloc_counter().load(); }
+
 int lc3d_host_register(void* ptr, uint64_t bytes) {
   if (!ptr || bytes == 0) return LC3D_ERR_INVALID;
   const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);

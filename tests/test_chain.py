@@ -6,6 +6,7 @@ import sys
 import tempfile
 
 import numpy as np
+import pytest
 
 from lowcost3dreconstruction_b200 import chain, synth
 
@@ -43,6 +44,7 @@ def test_record_roundtrip():
 WORKER = r'''
 import os, sys, json
 import numpy as np
+import pytest
 sys.path.insert(0, os.environ["LC3D_ROOT"])
 import torch.distributed as dist
 from lowcost3dreconstruction_b200 import chain, synth
@@ -122,3 +124,56 @@ def test_align_pairs_prefetch_matches_serial():
             assert sorted(gets) == need and sorted(rel) == need
             if pairs:
                 assert threads and threading.current_thread().name not in threads  # prepared off-thread
+
+
+def test_align_pairs_dag_each_view_once_and_same_records():
+    """chain.align_pairs_dag: every needed view is prepared exactly once and released exactly once
+    (after its last pair), records equal to the serial order, whatever the thread counts."""
+    import threading
+    import time
+
+    def run(pairs, n_prep, n_align):
+        gets, rel, busy, lock = [], [], {"max": 0, "now": 0}, threading.Lock()
+
+        def prep():
+            def get_view(v):
+                with lock:
+                    busy["now"] += 1
+                    busy["max"] = max(busy["max"], busy["now"])
+                time.sleep(0.003)
+                with lock:
+                    busy["now"] -= 1
+                gets.append(v)
+                return ("view", v)
+            return get_view
+
+        def align():
+            def f(s, t):
+                assert s[1] == t[1] + 1 and s[1] not in rel and t[1] not in rel  # never released while in use
+                time.sleep(0.002)
+                return dict(transformation=np.eye(4) * s[1], fitness=0.5 * s[1], iterations=3, converged=True, state=1)
+            return f
+
+        local = np.zeros((12, chain.RECORD))
+        chain.align_pairs_dag(pairs, [prep() for _ in range(n_prep)], [align() for _ in range(n_align)], local,
+                              release=lambda d: rel.append(d[1]))
+        return local, gets, rel, busy["max"]
+
+    for pairs in ([1, 2, 3, 4, 5, 6, 7], [4, 5], [9], []):
+        need = sorted(set(pairs) | {p - 1 for p in pairs})
+        ref = np.zeros((12, chain.RECORD))
+        chain.align_pairs(pairs, lambda v: ("view", v),
+                          lambda s, t: dict(transformation=np.eye(4) * s[1], fitness=0.5 * s[1], iterations=3,
+                                            converged=True, state=1), ref)
+        for n_prep, n_align in ((1, 1), (2, 2), (4, 3)):
+            loc, gets, rel, maxbusy = run(pairs, n_prep, n_align)
+            assert np.array_equal(loc, ref)
+            assert sorted(gets) == need and sorted(rel) == need
+            assert maxbusy <= n_prep
+            if len(need) >= 4 and n_prep >= 2:
+                assert maxbusy >= 2  # views really are prepared concurrently
+
+    def boom(v):
+        raise RuntimeError("prepare failed")
+    with pytest.raises(RuntimeError):
+        chain.align_pairs_dag([1, 2], [boom], [lambda s, t: {}], np.zeros((3, chain.RECORD)))
