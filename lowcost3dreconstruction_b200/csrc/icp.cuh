@@ -536,10 +536,12 @@ __device__ __forceinline__ void icp_block_row(double acc, double (*s_rows)[32], 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   s_rows[w][lane] = acc;
   __threadfence_block();
+  __syncwarp();  // every lane's row entry is ordered before lane 0's ticket (release)
   unsigned ticket = 0;
   if (lane == 0) ticket = atomicAdd(s_arrived, 1u);
   ticket = __shfl_sync(0xffffffffu, ticket, 0);
   if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
+    __syncwarp();  // ... and lane 0's ticket before every lane's reads (acquire)
     __threadfence_block();
     if (lane < NV) {
       double s = 0.0;

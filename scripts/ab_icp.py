@@ -23,12 +23,17 @@ src, tgt = bench.load_pair(0)
 ctx = api.Context(0)
 n_t, c_t = api.normals(tgt, 30, ctx=ctx)
 dS, dT = ctx.upload(HostCloud(src)), ctx.upload(HostCloud(tgt, normal=n_t, curvature=c_t))
+print("  inputs", hashlib.sha1(src.tobytes()).hexdigest()[:10], hashlib.sha1(tgt.tobytes()).hexdigest()[:10],
+      "normals", hashlib.sha1(n_t.tobytes()).hexdigest()[:10], flush=True)
 modes = %(modes)r
 for mode in modes:
-    rows = []
+    rows, seen = [], set()
     for rep in range(%(reps)d):
         r = api.icp_align(dS, dT, 0.02, 50, mode=mode, ctx=ctx)
         rows.append([r['ms']['index'], r['ms']['loop'], r['ms']['fitness'], r['ms']['total']])
+        seen.add((r['iterations'], r['last_correspondences'], r['fitness'], r['transformation'].tobytes()))
+    if len(seen) != 1:
+        print(f"  !! mode {mode}: {len(seen)} DISTINCT outcomes in {%(reps)d} repetitions", flush=True)
     a = np.array(rows[3:])
     h = hashlib.sha1(r['transformation'].tobytes()).hexdigest()[:10]
     print(f"  mode {mode}: it {r['iterations']} st {r['state']} corr {r['last_correspondences']} fit {r['fitness']:.9e} T#{h} | "
