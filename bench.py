@@ -357,11 +357,13 @@ def main():
     # host threads and pinned buffers next to the GPU: NVML's CPU affinity of the device (the cores of
     # its NUMA node).  The e2e arm is a host-side wall clock over PCIe copies from pinned memory; a
     # process that lands on the far socket sees 30 % less of it.
-    affinity = None
+    affinity, gpu_uuid = None, None
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        gpu_uuid = pynvml.nvmlDeviceGetUUID(h)
+        gpu_uuid = gpu_uuid.decode() if isinstance(gpu_uuid, bytes) else str(gpu_uuid)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
         cores &= set(os.sched_getaffinity(0))
@@ -610,7 +612,7 @@ def main():
                       "ms_normals_k30_host_call": ms_normals, "wall_s_timed_region": wall,
                       "fitness": results[-1]["fitness"], "state": results[-1]["state"],
                       "record_gather_ms_after_timed_region": gather_ms,
-                      "all_ranks_bit_identical_results": ranks_identical,
+                      "all_ranks_bit_identical_results": ranks_identical, "gpu_uuid_rank0": gpu_uuid,
                       "e2e_pcl_aos_pageable": {"value": e2e_aos, "unit": "iterations/s",
                                                "h2d_bytes_per_step": int(Sa.n * 48 + Ta.n * 48), "d2h_bytes_per_step": d2h,
                                                "host_memory": "pageable, 48-byte pcl::PointXYZRGBNormal AoS "
