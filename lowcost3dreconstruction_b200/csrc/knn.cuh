@@ -130,9 +130,10 @@ __device__ __forceinline__ void knn_sort_truncate(KnnState<CAP>& s, int lane) {
 
 // Exact kNN of (qx,qy,qz); on return s.buf[0..s.cnt) holds the neighbours ascending.
 // Warp-uniform.  k <= CAP - 32.  kfirst: first block half-width (cells), from the index density.
+// mask (nullable): only points whose ORIGINAL index has mask[index] != 0 exist for this search.
 template <int CAP>
 __device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, KnnState<CAP>& s,
-                                int lane, int kfirst) {
+                                int lane, int kfirst, const uint32_t* __restrict__ mask = nullptr) {
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
   s.cnt = 0;
@@ -215,6 +216,7 @@ __device__ void knn_search_warp(const GridDev& g, float qx, float qy, float qz, 
           const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
           key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
           pass = d2 <= rg2 && key < s.thresh;
+          if (mask && pass) pass = __ldg(&mask[__float_as_int(p.w)]) != 0u;
         }
         const unsigned m = __ballot_sync(full, pass);
         if (pass) s.buf[s.cnt + __popc(m & lt)] = key;
@@ -336,6 +338,20 @@ struct KnnArgs {
   float* out_curv;    // nq
   float vpx, vpy, vpz;
   int kfirst;  // first block half-width in cells (knn_kfirst)
+  // kConsumeSor, optional: the neighbour lists themselves (nq x k original indices, ascending
+  // (d2, index), -1 = none), for a later pass to reuse
+  int32_t* out_lists;
+  // kConsumeNormals on a SUBSET of the indexed cloud (lc3d_prepare_view: normals of the points SOR
+  // kept, on SOR's own index and neighbour lists): keep[i] != 0 marks the points that exist,
+  // remap[i] = output slot of query i, lists / list_k = neighbour lists of a k-NN pass over the whole
+  // cloud with list_k >= k.  The k nearest KEPT neighbours of a kept query are the first k kept
+  // entries of its list whenever the list holds that many (every kept point inside the list's
+  // radius is on the list, in the same (d2, index) order); otherwise the query is searched on the
+  // index with the mask.  All null / 0 for the plain pass.
+  const uint32_t* keep;
+  const uint32_t* remap;
+  const int32_t* lists;
+  int list_k;
 };
 
 template <int CAP, int CONSUMER>
@@ -356,7 +372,31 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_consta
   s.cnt = 0;
   s.thresh = kMaxKey;
   const bool ok = finite3(q.x, q.y, q.z);
-  if (ok) knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane, a.kfirst);
+  int oslot = oq;  // output slot
+  if (CONSUMER == kConsumeNormals && a.keep) {
+    if (__ldg(&a.keep[oq]) == 0u) return;  // the query itself was filtered out (warp-uniform)
+    oslot = (int)__ldg(&a.remap[oq]);
+    // the first k kept entries of the query's neighbour list
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int base = 0; base < a.list_k && cnt < a.k; base += 32) {
+      const int t = base + lane;
+      const int idx = t < a.list_k ? __ldg(&a.lists[(size_t)oq * a.list_k + t]) : -1;
+      const bool kp = idx >= 0 && __ldg(&a.keep[idx]) != 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, kp);
+      const int pos = cnt + __popc(m & lt);
+      if (kp && pos < a.k) s.buf[pos] = (unsigned long long)(unsigned)idx;  // the consumer reads the index only
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    if (cnt >= a.k) {
+      s.cnt = a.k;
+    } else if (ok) {  // too many of the listed neighbours were filtered out: exact masked search
+      knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane, a.kfirst, a.keep);
+    }
+  } else if (ok) {
+    knn_search_warp<CAP>(g, q.x, q.y, q.z, s, lane, a.kfirst);
+  }
   __syncwarp();
   if (CONSUMER == kConsumeIndices) {
     for (int t = lane; t < a.k; t += 32) {
@@ -383,6 +423,9 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_consta
       a.out_mean[oq] = md;
       a.out_valid[oq] = valid;
     }
+    if (a.out_lists)
+      for (int t = lane; t < a.k; t += 32)
+        a.out_lists[(size_t)oq * a.k + t] = t < s.cnt ? (int)(unsigned)(s.buf[t] & 0xffffffffu) : -1;
   } else {
     // gather the neighbours' coordinates in parallel, then accumulate the 9 float32 sums of
     // computeMeanAndCovarianceMatrix sequentially in neighbour order (lane a owns sum a)
@@ -438,10 +481,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const __grid_consta
         ny = v[1];
         nz = v[2];
       }
-      a.out_normal[3 * (size_t)oq + 0] = nx;
-      a.out_normal[3 * (size_t)oq + 1] = ny;
-      a.out_normal[3 * (size_t)oq + 2] = nz;
-      a.out_curv[oq] = curv;
+      a.out_normal[3 * (size_t)oslot + 0] = nx;
+      a.out_normal[3 * (size_t)oslot + 1] = ny;
+      a.out_normal[3 * (size_t)oslot + 2] = nz;
+      a.out_curv[oslot] = curv;
     }
   }
 }
