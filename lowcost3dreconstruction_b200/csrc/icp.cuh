@@ -526,29 +526,43 @@ __device__ __forceinline__ double icp_estimator_acc(const GridDev& g, bool has, 
   return warp_reduce_scatter32([&](int i) { return p2p_value(i, sv, dv, d2v, one); }, lane);
 }
 
-// One partial row per BLOCK (value-major) without a block barrier: every warp parks its row in
-// shared memory and retires; the LAST warp to arrive (shared-memory ticket) adds the rows in warp
-// order (fixed order: deterministic) and writes the block's row.  Warps still retire independently,
-// and the solve kernel reads 4x fewer rows.
+// One partial row per BLOCK (value-major) without stalling the warps on a block barrier: every warp
+// parks its row in shared memory; warps 1.. then ARRIVE at a named barrier and retire, warp 0 WAITS
+// on it (a waiting warp takes no issue slot, and the block's registers are held until its slowest
+// warp is done anyway), adds the rows in warp order (fixed order: deterministic) and writes the
+// block's row.  The solve kernel reads 4x fewer rows.  (An earlier version let the LAST warp to
+// arrive do the sum, ordered by __threadfence_block + a shared-memory ticket; same cost, but the
+// named barrier is an ordering the hardware and compute-sanitizer both understand.)
+#ifndef LC3D_ROW_TICKET
+#define LC3D_ROW_TICKET 0
+#endif
 template <int NV>
 __device__ __forceinline__ void icp_block_row(double acc, double (*s_rows)[32], unsigned* s_arrived,
                                               double* __restrict__ partials) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   s_rows[w][lane] = acc;
   __threadfence_block();
-  __syncwarp();  // every lane's row entry is ordered before lane 0's ticket (release)
+#if LC3D_ROW_TICKET
+  __syncwarp();
   unsigned ticket = 0;
   if (lane == 0) ticket = atomicAdd(s_arrived, 1u);
   ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  if (ticket == (unsigned)(kIcpThreads / 32 - 1)) {
-    __syncwarp();  // ... and lane 0's ticket before every lane's reads (acquire)
-    __threadfence_block();
-    if (lane < NV) {
-      double s = 0.0;
+  if (ticket != (unsigned)(kIcpThreads / 32 - 1)) return;
+  __syncwarp();
+  __threadfence_block();
+#else
+  (void)s_arrived;
+  if (w != 0) {
+    asm volatile("bar.arrive 1, %0;" ::"n"(kIcpThreads) : "memory");
+    return;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kIcpThreads) : "memory");
+#endif
+  if (lane < NV) {
+    double s = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += ((volatile double*)s_rows[ww])[lane];
-      partials[(size_t)lane * gridDim.x + blockIdx.x] = s;
-    }
+    for (int ww = 0; ww < kIcpThreads / 32; ++ww) s += ((volatile double*)s_rows[ww])[lane];
+    partials[(size_t)lane * gridDim.x + blockIdx.x] = s;
   }
 }
 
