@@ -59,6 +59,7 @@ const unsigned char* stage_raw(lc3d_ctx* ctx, DevBuf& buf, const void* host, int
   size_t bytes = (size_t)(n - 1) * stride + rec;
   buf.ensure(bytes + 64);
   LC3D_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, cs ? cs : ctx->stream));
+  ctx->h2d_bytes_call += bytes;
   return buf.as<unsigned char>();
 }
 
@@ -116,6 +117,7 @@ const unsigned char* stage_packed(lc3d_ctx* ctx, int slot, DevBuf& buf, const vo
     throw CudaError{"staged upload failed"};
   }
   LC3D_CUDA(cudaEventRecord(ctx->stage_done[slot], st));
+  ctx->h2d_bytes_call += (size_t)n * 12;
   return dev;
 }
 
@@ -329,14 +331,19 @@ void icp_run(lc3d_ctx* ctx, const lc3d_dcloud* src, const lc3d_dcloud* tgt, cons
   }
   grid_plan(ctx, G, tgt->xyz.as<float4>(), tgt->n, cell_factor_env(), 0.0, xsub_env(),
             hint.nfinite > 0 ? &hint : nullptr);
-  // host-buffer point-to-plane, LC3D_DEFER_NORMALS=1 (for hosts with a slow PCIe link): while the
-  // target normals are still in flight, build the index and run the search of iteration 0 without
-  // them, gather them into index order afterwards and let icp_estimate_kernel compute iteration 0's
-  // sums.  Off by default: at the 43 GB/s these boxes move, the normals land 40 us after the index
-  // is built and the extra gather + estimate launches cost 30 us (profiles/r02_summary.md).
+  // host-buffer point-to-plane on a slow PCIe link: while the target normals are still in flight,
+  // build the index and run the search of iteration 0 without them, gather them into index order
+  // afterwards and let icp_estimate_kernel compute iteration 0's sums.  At 43 GB/s the normals land
+  // 40 us after the index is built and the extra gather + estimate launches cost 30 us: no gain; at
+  // 25 GB/s (the same box type, another host) they land 200 us later (profiles/r02_summary.md).
+  // LC3D_DEFER_NORMALS=0/1 forces the choice.
+  // Default: decided by the host->device rate the previous host-buffer call on this context measured —
+  // below kDeferBelowGbs the normals are the last thing the first iteration would wait for.
+  constexpr double kDeferBelowGbs = 35.0;
+  bool want_defer = ctx->h2d_gbs > 0.0 && ctx->h2d_gbs < kDeferBelowGbs;
+  if (const char* e = std::getenv("LC3D_DEFER_NORMALS")) want_defer = std::atoi(e) != 0;
   const bool defer_normals = hooks.before_target_normals && p->mode == LC3D_ICP_POINT_TO_PLANE && tgt->has_normal &&
-                             tgt->n > 0 && n > 0 && !sharded && !std::getenv("LC3D_STATS") &&
-                             std::getenv("LC3D_DEFER_NORMALS") && std::atoi(std::getenv("LC3D_DEFER_NORMALS")) != 0;
+                             tgt->n > 0 && n > 0 && !sharded && !std::getenv("LC3D_STATS") && want_defer;
   const bool two_streams = ctx->aux_stream != nullptr && !std::getenv("LC3D_NO_AUX");
   {
     struct StreamSwap {
@@ -768,6 +775,8 @@ void lc3d_destroy(lc3d_ctx* ctx) {
   for (auto& b : ctx->stage) b.release();
   for (auto& e : ctx->stage_done)
     if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_h2d)
+    if (e) cudaEventDestroy(e);
   delete ctx->host_pool;
   ctx->tmp_a.release();
   ctx->tmp_b.release();
@@ -882,13 +891,18 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
     // (first read after the loop).  Each array is unpacked, stream-ordered, right before its
     // first use.
     cudaStream_t cs = ctx->copy_stream;
+    ctx->h2d_bytes_call = 0;
+    for (auto& e : ctx->ev_h2d)
+      if (!e) LC3D_CUDA(cudaEventCreate(&e));
     try {
+      LC3D_CUDA(cudaEventRecord(ctx->ev_h2d[0], cs ? cs : ctx->stream));
       PendingUpload pt = upload_begin(ctx, target, &tc.b, params->mode == LC3D_ICP_POINT_TO_PLANE,
                                       ctx->scratch[kScrRawA], ctx->scratch[kScrRawB], cs, ctx->ev_up[0], true);
       PendingUpload ps = upload_begin(ctx, source, &tc.a, need_src_normals, ctx->scratch[kScrRawC],
                                       ctx->scratch[kScrRawD], cs, ctx->ev_up[1], true);
       upload_begin_normals(ctx, pt, ctx->scratch[kScrRawB], cs, ctx->ev_up[2]);
       upload_begin_normals(ctx, ps, ctx->scratch[kScrRawD], cs, ctx->ev_up[3]);
+      LC3D_CUDA(cudaEventRecord(ctx->ev_h2d[1], cs ? cs : ctx->stream));
       upload_finish(ctx, pt);
       ctx->tm[0].stop(ctx->stream);
       IcpHooks hooks;
@@ -899,6 +913,12 @@ int lc3d_icp_align(lc3d_ctx* ctx, const lc3d_cloud* source, const lc3d_cloud* ta
       // every staged copy has been consumed on the paths above except in odd output
       // combinations (normals requested without xyz): never return with a copy in flight
       if (cs) LC3D_CUDA(cudaStreamSynchronize(cs));
+      // the rate the four uploads achieved back to back on the copy stream (only meaningful when it
+      // carried nothing else: the separate copy stream, pinned or packed-staged sources)
+      float ms_h2d = 0.0f;
+      if (cs && ctx->h2d_bytes_call >= ((size_t)4 << 20) &&
+          cudaEventElapsedTime(&ms_h2d, ctx->ev_h2d[0], ctx->ev_h2d[1]) == cudaSuccess && ms_h2d > 0.0f)
+        ctx->h2d_gbs = (double)ctx->h2d_bytes_call / ((double)ms_h2d * 1e6);
     } catch (...) {
       if (cs) cudaStreamSynchronize(cs);  // no copy may still read the caller's buffers
       throw;

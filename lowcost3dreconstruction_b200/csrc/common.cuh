@@ -319,6 +319,12 @@ struct lc3d_ctx {
   lc3d::BufPool pool;          // parked buffers of freed resident clouds
   // pageable host clouds: packed by host threads into pinned staging memory, chunk by chunk, each
   // chunk's DMA overlapping the packing of the next (slots: target xyz / normals, source xyz / normals)
+  // host->device rate seen by the previous host-buffer alignment (GB/s, 0 = unknown) and this
+  // call's staged bytes: PCIe differs 2x between otherwise identical boxes, and the alignment
+  // schedules itself around the uploads (icp_run: iteration 0 before the target normals arrive)
+  double h2d_gbs = 0.0;
+  size_t h2d_bytes_call = 0;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   lc3d::PinnedBuf stage[4];
   cudaEvent_t stage_done[4] = {nullptr, nullptr, nullptr, nullptr};  // last DMA out of the slot
   lc3d::HostPool* host_pool = nullptr;

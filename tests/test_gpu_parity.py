@@ -265,6 +265,22 @@ def test_icp_packed_staging_of_pageable_aos_records(ctx, pair_normals, monkeypat
         assert np.array_equal(g["registered_normal"], ref["registered_normal"])
 
 
+def test_icp_deferred_target_normals_same_bits(ctx, pair_normals, monkeypatch):
+    """Host-buffer point-to-plane ICP with iteration 0 searched before the target normals arrive
+    (SEARCH_ONLY kernel + gather_normals_sorted + icp_estimate_kernel; chosen at run time from the
+    measured PCIe rate) gives the same bits as the fused first iteration."""
+    src, tgt = pair_normals
+    out = {}
+    for mode_env in ("0", "1"):
+        monkeypatch.setenv("LC3D_DEFER_NORMALS", mode_env)
+        out[mode_env] = api.icp_align(src, tgt, 0.02, 30, mode=1, dump_iteration=0, want_registered=True, ctx=ctx)
+    a, b = out["0"], out["1"]
+    assert a["iterations"] == b["iterations"] and a["state"] == b["state"] and a["fitness"] == b["fitness"]
+    assert np.array_equal(a["transformation"], b["transformation"])
+    assert np.array_equal(a["corr_index"], b["corr_index"]) and np.array_equal(a["corr_dist2"], b["corr_dist2"])
+    assert np.array_equal(a["registered_xyz"], b["registered_xyz"])
+
+
 def test_icp_pinned_and_pageable_host_buffers_agree(ctx, pair_normals):
     """Host-buffer ICP takes two upload paths: page-locked memory goes out with plain async copies
     of the caller's records, pageable memory is packed by the host thread pool into pinned staging
