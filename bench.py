@@ -434,9 +434,13 @@ def main():
     tmax, tsum = t.clone(), t.clone()
     gather_ms = 0.0
     ranks_identical = True
+    per_rank_ms = [ms_steps / args.steps]
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        allt = torch.empty(world, 3, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt.view(-1), t)
+        per_rank_ms = [float(x) / args.steps for x in allt[:, 0].cpu()]
         # the one exchange of the run: every step's 4x4 (+ fitness, iterations) from every rank;
         # rank 0 checks that every GPU produced the same bits
         mine = torch.tensor(np.stack([np.concatenate([r["transformation"].reshape(16).astype(np.float64),
@@ -613,6 +617,7 @@ def main():
                       "fitness": results[-1]["fitness"], "state": results[-1]["state"],
                       "record_gather_ms_after_timed_region": gather_ms,
                       "all_ranks_bit_identical_results": ranks_identical, "gpu_uuid_rank0": gpu_uuid,
+                      "ms_per_step_by_rank": [round(x, 4) for x in per_rank_ms],
                       "e2e_pcl_aos_pageable": {"value": e2e_aos, "unit": "iterations/s",
                                                "h2d_bytes_per_step": int(Sa.n * 48 + Ta.n * 48), "d2h_bytes_per_step": d2h,
                                                "host_memory": "pageable, 48-byte pcl::PointXYZRGBNormal AoS "

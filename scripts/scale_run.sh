@@ -10,7 +10,7 @@ run() {
 import json
 d = json.load(open("gpurun_out/n${N}_bench$tag.json")); c = d["extra"]["chain"]
 print("N=${N}$tag value", round(d["value"]), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"]), d["e2e"].get("pcie_pinned_gbs"), "chain pairs/s", round(c["pairs_per_sec"], 1),
-      "ms/chain", round(c["seconds_per_chain"] * 1e3, 2), "lanes", c["lanes_per_gpu"], c["rank0_seconds_per_repetition"], "identical", d["extra"].get("all_ranks_bit_identical_results"))
+      "ms/chain", round(c["seconds_per_chain"] * 1e3, 2), "lanes", c["lanes_per_gpu"], c["rank0_seconds_per_repetition"], "identical", d["extra"].get("all_ranks_bit_identical_results"), "by rank", d["extra"].get("ms_per_step_by_rank"))
 PY
 }
 nproc
