@@ -177,3 +177,39 @@ def test_align_pairs_dag_each_view_once_and_same_records():
         raise RuntimeError("prepare failed")
     with pytest.raises(RuntimeError):
         chain.align_pairs_dag([1, 2], [boom], [lambda s, t: {}], np.zeros((3, chain.RECORD)))
+
+
+def test_align_pairs_lanes_split_and_records():
+    """chain.align_pairs_lanes: contiguous sub-blocks, one per lane, each lane's callables used only
+    by its own thread; records equal to the serial order; one extra view per additional lane."""
+    import threading
+
+    def lane():
+        seen_threads, gets = set(), []
+
+        def get_view(v):
+            seen_threads.add(threading.current_thread().name)
+            gets.append(v)
+            return ("view", v)
+
+        def align(s, t):
+            seen_threads.add(threading.current_thread().name)
+            assert s[1] == t[1] + 1
+            return dict(transformation=np.eye(4) * s[1], fitness=0.5 * s[1], iterations=3, converged=True, state=1)
+
+        return (get_view, align, lambda d: None), seen_threads, gets
+
+    pairs = list(range(1, 12))
+    ref = np.zeros((12, chain.RECORD))
+    chain.align_pairs(pairs, lambda v: ("view", v),
+                      lambda s, t: dict(transformation=np.eye(4) * s[1], fitness=0.5 * s[1], iterations=3,
+                                        converged=True, state=1), ref)
+    for n_lanes in (1, 2, 3):
+        lanes = [lane() for _ in range(n_lanes)]
+        local = np.zeros((12, chain.RECORD))
+        chain.align_pairs_lanes(pairs, [ln[0] for ln in lanes], local, prefetch=1)
+        assert np.array_equal(local, ref)
+        assert sum(len(ln[2]) for ln in lanes) == len(pairs) + n_lanes  # border views prepared once per lane
+        blocks = [sorted(ln[2]) for ln in lanes]
+        for b in blocks:
+            assert b == list(range(b[0], b[-1] + 1))  # contiguous
