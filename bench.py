@@ -424,6 +424,10 @@ def main():
             dist.barrier()
         wall = time.perf_counter() - wall0
     launches = ctx.launch_count - l0
+    # every step aligns the same resident pair: anything but identical bits would be a defect
+    steps_identical = all(np.array_equal(r["transformation"], results[0]["transformation"]) and
+                          r["fitness"] == results[0]["fitness"] and r["iterations"] == results[0]["iterations"] and
+                          r["last_correspondences"] == results[0]["last_correspondences"] for r in results)
     clocks = sampler.stop()
     ms_steps = sum(a.elapsed_time(b) for a, b in ev)
     iters = sum(r["iterations"] for r in results)
@@ -616,7 +620,8 @@ def main():
                       "ms_normals_k30_host_call": ms_normals, "wall_s_timed_region": wall,
                       "fitness": results[-1]["fitness"], "state": results[-1]["state"],
                       "record_gather_ms_after_timed_region": gather_ms,
-                      "all_ranks_bit_identical_results": ranks_identical, "gpu_uuid_rank0": gpu_uuid,
+                      "all_ranks_bit_identical_results": ranks_identical, "all_steps_bit_identical_results": bool(steps_identical),
+                      "last_correspondences": int(results[-1]["last_correspondences"]), "gpu_uuid_rank0": gpu_uuid,
                       "ms_per_step_by_rank": [round(x, 4) for x in per_rank_ms],
                       "e2e_pcl_aos_pageable": {"value": e2e_aos, "unit": "iterations/s",
                                                "h2d_bytes_per_step": int(Sa.n * 48 + Ta.n * 48), "d2h_bytes_per_step": d2h,
