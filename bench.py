@@ -47,7 +47,7 @@ CHAIN_STEP = 360.0 / CHAIN_VIEWS
 CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL = 0.002, 50, 1.0
 CHAIN_PREFETCH = int(os.environ.get("LC3D_CHAIN_PREFETCH", "1"))  # views prepared ahead on a worker thread (0 = serial)
 CHAIN_LANES = int(os.environ.get("LC3D_CHAIN_LANES", "3"))  # host threads (pair sub-blocks) per GPU
-CHAIN_MODE = os.environ.get("LC3D_CHAIN_MODE", "dag")
+CHAIN_MODE = os.environ.get("LC3D_CHAIN_MODE", "native")  # native | dag | lanes
 CHAIN_PREP = int(os.environ.get("LC3D_CHAIN_PREP", "4"))    # dag mode: view-preparation threads per GPU
 CHAIN_ALIGN = int(os.environ.get("LC3D_CHAIN_ALIGN", "3"))  # dag mode: pair-alignment threads per GPU
 
@@ -223,13 +223,18 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     # prepare views, CHAIN_ALIGN threads align pairs as soon as both views are ready; every thread has
     # its own lc3d context (own stream, own scratch).  LC3D_CHAIN_MODE=lanes selects the sub-block
     # pipelines of chain.align_pairs_lanes instead.
-    dag = CHAIN_MODE == "dag"
+    native = CHAIN_MODE == "native"  # the same task graph run by the library's own host threads (lc3d_chain_run)
+    dag = CHAIN_MODE == "dag" or native
     n_lanes = max(1, min(CHAIN_LANES, len(pairs) // 2))
     n_prep = max(1, min(CHAIN_PREP, len(pairs) + 1)) if dag else n_lanes
     n_align = max(1, min(CHAIN_ALIGN, len(pairs))) if dag else n_lanes
-    icp_ctx = [ctx] + [api.Context(ctx.device) for _ in range(n_align - 1)]
-    prep_ctx = [api.Context(ctx.device) for _ in range(n_prep)]
+    icp_ctx = [ctx] + ([] if native else [api.Context(ctx.device) for _ in range(n_align - 1)])
+    prep_ctx = [] if native else [api.Context(ctx.device) for _ in range(n_prep)]
     pinned = {v: api.host_register(a) for v, a in raw.items()}  # the PLY loader's buffers, pinned once
+    nat = chain.NativeChain(ctx.device, n_prep, n_align) if native else None
+    nat_views = [pinned[v] for v in range(pairs[0] - 1, pairs[-1] + 1)] if native and pairs else []
+    nat_kw = dict(leaf_size=CHAIN_LEAF, sor_mean_k=CHAIN_SOR_K, sor_stddev_mul=CHAIN_SOR_MUL, normals_k=K_NORMALS,
+                  max_correspondence_distance=MAX_CORR, max_iterations=MAX_ITER, mode=api.POINT_TO_PLANE)
 
     def one_chain():
         """this rank's views prepared on the device, its pairs aligned resident"""
@@ -247,7 +252,13 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
                 return api.icp_align(src, tgt, MAX_CORR, MAX_ITER, mode=api.POINT_TO_PLANE, ctx=icp_ctx[i])
             return align
 
-        if dag:
+        if native:
+            if nat_views:
+                res_, np_ = nat.run(nat_views, **nat_kw)
+                for i_, r_ in enumerate(res_):
+                    local[pairs[0] - 1 + i_] = chain.pack_record(r_)
+                npts.extend(np_)
+        elif dag:
             chain.align_pairs_dag(pairs, [prep_fn(i) for i in range(n_prep)], [align_fn(i) for i in range(n_align)],
                                   local, release=lambda d: d.free())
         else:
@@ -264,7 +275,10 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
     # device-wide synchronisation, 5-25 ms when seven streams are busy): every context sees every view /
     # pair of the block once, so that the timed repetitions allocate nothing
     # (rank0_device_allocations_per_repetition).  Then two whole chains (NCCL communicator, pools).
-    if dag:
+    if native:
+        if nat_views:
+            nat.run(nat_views, warm=True, **nat_kw)
+    elif dag:
         for c in prep_ctx:
             held = {v: api.prepare_view(pinned[v], CHAIN_LEAF, CHAIN_SOR_K, CHAIN_SOR_MUL, K_NORMALS, ctx=c)[0]
                     for v in sorted({p for p in pairs} | {p - 1 for p in pairs})}
@@ -296,6 +310,8 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
         api.host_unregister(a)
     for c in prep_ctx + icp_ctx[1:]:
         c.close()
+    if nat:
+        nat.close()
     if rank != 0:
         return None
     dt = float(tt[0])
@@ -313,7 +329,8 @@ def run_chain(ctx, rank, world, dev, pairs, raw, resid, reps: int) -> dict | Non
             "median_rot_err_deg_vs_truth": float(np.median(errs)), "max_rot_err_deg_vs_truth": float(np.max(errs)),
             "points_per_view_after_voxel_sor": int(np.mean(npts)) if npts else 0,
             "pose_35_translation_m": [float(x) for x in poses[-1][:3, 3]],
-            "schedule": (f"task graph: {n_prep} view-preparation + {n_align} pair-alignment host threads per GPU" if dag
+            "schedule": (f"task graph: {n_prep} view-preparation + {n_align} pair-alignment host threads per GPU"
+                         + (" (native executor, lc3d_chain_run)" if native else " (Python threads)") if dag
                          else f"{n_lanes} sub-block pipelines per GPU, prefetch {CHAIN_PREFETCH}"),
             "prefetch_views": CHAIN_PREFETCH, "lanes_per_gpu": n_lanes,
             "rank0_seconds_per_repetition": [round(x, 5) for x in rep_s],

@@ -270,6 +270,25 @@ int lc3d_prepare_view(lc3d_ctx* ctx, const lc3d_cloud* cloud, const lc3d_prepare
 int lc3d_cloud_download(lc3d_ctx* ctx, const lc3d_dcloud* dc, float* out_xyz, float* out_normal,
                         float* out_curvature);
 
+/* ------------------------------------------------------- view chain on one device ----- */
+
+/* The pair block of a turntable chain as a task graph on ONE device (scripts/alignment.sh:99-113 and
+ * the :123-126 TODO, per GPU): every view prepared once (lc3d_prepare_view), every pair aligned as
+ * soon as both of its views are ready (lc3d_icp_align_resident), on prepare_threads + align_threads
+ * host threads that each own an lc3d_ctx (own stream, own scratch).  The executor keeps its contexts
+ * between runs, so a steady stream of chains allocates nothing. */
+typedef struct lc3d_chain lc3d_chain;
+int lc3d_chain_create(int device, int32_t prepare_threads, int32_t align_threads, lc3d_chain** out);
+void lc3d_chain_destroy(lc3d_chain* chain);
+const char* lc3d_chain_last_error(const lc3d_chain* chain);
+/* views[0..n_views): host clouds (xyz) of consecutive views; pair i (0 <= i < n_views - 1) registers
+ * view i+1 (source) onto view i (target).  results[n_views - 1]; points_per_view[n_views] (may be
+ * NULL) = points of every prepared view.  warm != 0: instead of the task graph, EVERY context
+ * prepares every view / aligns every pair once (scratch buffers grow to their final sizes; the
+ * results are still written).  Returns LC3D_OK or the first error (lc3d_chain_last_error). */
+int lc3d_chain_run(lc3d_chain* chain, const lc3d_cloud* views, int32_t n_views, const lc3d_prepare_params* prepare,
+                   const lc3d_icp_params* icp, lc3d_icp_result* results, int64_t* points_per_view, int32_t warm);
+
 /* ------------------------------------------------------------ transform ----- */
 
 /* pcl::transformPointCloudWithNormals (pcl_tools/transform.cpp:84-90; SURVEY §8f

@@ -89,6 +89,7 @@ STATE_NAMES = {0: "NOT_CONVERGED", 1: "ITERATIONS", 2: "TRANSFORM", 3: "ABS_MSE"
 SYMBOLS = [
     "lc3d_create", "lc3d_destroy", "lc3d_last_error", "lc3d_version", "lc3d_launch_count",
     "lc3d_debug_grid_info", "lc3d_debug_alloc_count",
+    "lc3d_chain_create", "lc3d_chain_destroy", "lc3d_chain_last_error", "lc3d_chain_run",
     "lc3d_cloud_upload", "lc3d_cloud_free", "lc3d_dcloud_size",
     "lc3d_icp_align", "lc3d_icp_align_resident",
     "lc3d_knn", "lc3d_nn", "lc3d_normals", "lc3d_centroid",
@@ -162,6 +163,15 @@ def _declare(lib):
     lib.lc3d_debug_grid_info.restype = None
     lib.lc3d_debug_alloc_count.argtypes = []
     lib.lc3d_debug_alloc_count.restype = i64
+    lib.lc3d_chain_create.argtypes = [C.c_int, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.lc3d_chain_create.restype = C.c_int
+    lib.lc3d_chain_destroy.argtypes = [vp]
+    lib.lc3d_chain_destroy.restype = None
+    lib.lc3d_chain_last_error.argtypes = [vp]
+    lib.lc3d_chain_last_error.restype = C.c_char_p
+    lib.lc3d_chain_run.argtypes = [vp, C.POINTER(Cloud), C.c_int32, C.POINTER(PrepareParams), C.POINTER(IcpParams),
+                                   C.POINTER(IcpResult), C.POINTER(i64), C.c_int32]
+    lib.lc3d_chain_run.restype = C.c_int
     lib.lc3d_cloud_upload.argtypes = [vp, cp, C.POINTER(vp)]
     lib.lc3d_cloud_upload.restype = C.c_int
     lib.lc3d_cloud_free.argtypes = [vp, vp]

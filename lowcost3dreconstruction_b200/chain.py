@@ -214,6 +214,54 @@ def align_pairs_dag(pairs: Sequence[int], prep_fns: Sequence[Callable[[int], obj
             raise err
 
 
+class NativeChain:
+    """The same task graph run by the library's own host threads (include/lc3d.h: lc3d_chain_*): one C
+    call per pair block, no interpreter between the tasks.  views: host xyz arrays of consecutive
+    views; pair i registers view i+1 onto view i."""
+
+    def __init__(self, device: int = 0, prepare_threads: int = 4, align_threads: int = 3):
+        import ctypes as C
+
+        from . import _capi
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        rc = self._lib.lc3d_chain_create(int(device), int(prepare_threads), int(align_threads), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"lc3d_chain_create failed ({rc}): {self._lib.lc3d_last_error(None).decode()}")
+        self._h = h
+
+    def run(self, views, leaf_size=0.0, sor_mean_k=0, sor_stddev_mul=1.0, normals_k=0, viewpoint=(0.0, 0.0, 0.0),
+            max_correspondence_distance=0.1, max_iterations=50, transformation_epsilon=1e-9,
+            euclidean_fitness_epsilon=1e-3, mode=0, warm=False):
+        """Returns (list of api.icp_align-style result dicts, one per pair; points per prepared view)."""
+        import ctypes as C
+
+        from . import _capi, api
+        hcs = [v if isinstance(v, _capi.HostCloud) else _capi.HostCloud(v) for v in views]
+        arr = (_capi.Cloud * len(hcs))(*[h.struct for h in hcs])
+        pp = _capi.PrepareParams(float(leaf_size), int(sor_mean_k), float(sor_stddev_mul), int(normals_k),
+                                 (C.c_float * 3)(*[float(x) for x in viewpoint]))
+        ip = _capi.IcpParams(float(max_correspondence_distance), float(transformation_epsilon),
+                             float(euclidean_fitness_epsilon), int(max_iterations), int(mode), 1, -1)
+        res = (_capi.IcpResult * (len(hcs) - 1))()
+        npts = (C.c_int64 * len(hcs))()
+        rc = self._lib.lc3d_chain_run(self._h, arr, len(hcs), C.byref(pp), C.byref(ip), res, npts, int(bool(warm)))
+        if rc != 0:
+            raise RuntimeError(f"lc3d_chain_run failed ({rc}): {self._lib.lc3d_chain_last_error(self._h).decode()}")
+        return [api._result_dict(r) for r in res], [int(x) for x in npts]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lc3d_chain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def register_chain(n_views: int, get_view: Callable[[int], object], align: Callable[[object, object], dict],
                    rank: int = 0, world: int = 1, device=None, prefetch: int = 0,
                    release: Callable[[object], None] | None = None) -> dict:

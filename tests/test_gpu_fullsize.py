@@ -142,3 +142,30 @@ def test_normal_estimation_centroid_flag(tmp_path, ctx):
     # pointing away from the centroid: outward for a convex-ish object
     inner = np.einsum("ij,ij->i", -nrm.astype(np.float64), xyz.astype(np.float64) - c[:3].astype(np.float64))
     assert np.nanmean(inner > 0) > 0.95
+
+
+def test_native_chain_executor_matches_stage_calls(ctx):
+    """lc3d_chain_run (the pair block as a task graph on the library's own host threads) returns, for
+    every pair, the bits of lc3d_prepare_view + lc3d_icp_align_resident called one after the other."""
+    from lowcost3dreconstruction_b200 import chain
+    views = [synth.apply_transform(synth.turntable_prior(v, 10.0), synth.kinect_view(v, step_deg=10.0, backdrop="none", scale=0.5))
+             for v in range(5)]
+    kw = dict(leaf_size=0.004, sor_mean_k=30, sor_stddev_mul=1.0, normals_k=20)
+    prepared = [api.prepare_view(v, kw["leaf_size"], kw["sor_mean_k"], kw["sor_stddev_mul"], kw["normals_k"], ctx=ctx)
+                for v in views]
+    ref = [api.icp_align(prepared[i + 1][0], prepared[i][0], 0.02, 50, mode=api.POINT_TO_PLANE, ctx=ctx) for i in range(4)]
+    nat = chain.NativeChain(0, prepare_threads=3, align_threads=2)
+    try:
+        for warm in (True, False, False):
+            res, npts = nat.run(views, max_correspondence_distance=0.02, max_iterations=50, mode=api.POINT_TO_PLANE,
+                                warm=warm, **kw)
+            assert npts == [p[1][2] for p in prepared]
+            for r, g in zip(ref, res):
+                assert np.array_equal(r["transformation"], g["transformation"]) and r["fitness"] == g["fitness"]
+                assert r["iterations"] == g["iterations"] and r["state"] == g["state"]
+        with pytest.raises(RuntimeError):
+            nat.run(views, mode=api.POINT_TO_PLANE)  # point-to-plane without normals: error surfaces, nothing hangs
+    finally:
+        nat.close()
+    for p in prepared:
+        p[0].free()
